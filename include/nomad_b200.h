@@ -1,0 +1,125 @@
+/* nomad_b200 -- C ABI of the B200-native NOMAD scoring + loss hot path.
+ *
+ * The reference (alessandroragano/nomad) has no FFI of its own: the seam is the set of Python
+ * attribute calls inside ``Nomad`` (reference src/nomad_audio/nomad.py).  Each entry point below
+ * replaces one of those calls; the cited lines are the reference interface it stands in for.
+ * ``INTEGRATION.md`` shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; ``nomad_b200_last_error()`` then
+ *     returns a thread-local, human-readable message.
+ *   - "device" pointers are CUDA device pointers into caller-owned memory (e.g. torch tensors'
+ *     data_ptr()); ``stream`` is a ``cudaStream_t`` passed as ``void*``.  Work is enqueued on that
+ *     stream; no entry point synchronises the device except the ``*_host`` variants, which take HOST
+ *     buffers, copy in, run, copy out and synchronise the stream before returning.
+ *   - the library owns no activation memory: the caller provides a workspace whose size the
+ *     matching ``*_workspace_bytes`` call reports (plain pointers and sizes, no torch types).
+ *   - one handle per (process, device); a handle is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef NOMAD_B200_H
+#define NOMAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NOMAD_B200_API __attribute__((visibility("default")))
+#else
+#define NOMAD_B200_API
+#endif
+
+#define NOMAD_B200_EMB_DIM 256   /* nomad.py:55  EMB_DIM     */
+#define NOMAD_B200_SSL_DIM 768   /* nomad.py:54  SSL_OUT_DIM */
+#define NOMAD_B200_NUM_LAYERS 12
+#define NOMAD_B200_MIN_SAMPLES 400 /* shortest waveform the conv encoder accepts (1 frame) */
+
+typedef struct nomad_b200_handle nomad_b200_handle;
+
+/* One named fp32 tensor of the checkpoint, HOST memory, contiguous, fairseq key names exactly as in
+ * ``TripletModel.state_dict()`` (reference nomad.py:65, train_triplet.py:177), e.g.
+ * "ssl_model.encoder.layers.3.fc1.weight", "embedding_layer.1.bias". */
+typedef struct {
+    const char* name;
+    const float* data;
+    int64_t numel;
+} nomad_b200_tensor;
+
+/* GEMM back end selector (``gemm_impl``): the tensor-core kernel is the product; the SIMT kernel
+ * exists so the GPU tests can cross-check it on device. */
+#define NOMAD_B200_GEMM_TCGEN05 0
+#define NOMAD_B200_GEMM_SIMT 1
+
+NOMAD_B200_API const char* nomad_b200_last_error(void);
+NOMAD_B200_API const char* nomad_b200_version(void);
+
+/* Replaces model construction + ``load_state_dict`` (nomad.py:53-68).  Folds weight-norm, permutes
+ * conv weights to K-major, fuses q/k/v, converts to bf16 and uploads to ``device``. */
+NOMAD_B200_API int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors, int device);
+NOMAD_B200_API int nomad_b200_destroy(nomad_b200_handle* h);
+NOMAD_B200_API int nomad_b200_set_gemm_impl(nomad_b200_handle* h, int gemm_impl);
+
+/* Replaces the fresh ``nn.Linear(768, 256)`` of ``LossNetLayers`` (nomad.py:238-241): head used by the
+ * 13th loss term.  Host pointers: w [256*768] row-major (out, in), b [256]. */
+NOMAD_B200_API int nomad_b200_set_loss_head(nomad_b200_handle* h, const float* w, const float* b);
+
+/* ---- scoring: ``TripletModel.forward`` for a batch of variable-length utterances -----------------
+ * Replaces the per-file loop ``model(wave, lengths)`` of nomad.py:166-189 / 224-231.
+ * ``wav`` is the concatenation of the B waveforms (fp32 mono 16 kHz); utterance i is
+ * wav[sample_offsets[i] .. sample_offsets[i+1]).  ``sample_offsets`` is a HOST array of B+1 entries.
+ * Every utterance is embedded exactly as if it were run alone (length-masked GroupNorm, positional
+ * conv, attention and pooling).  ``emb`` receives B x 256 unit-norm fp32 rows.
+ * Fails if an utterance is shorter than NOMAD_B200_MIN_SAMPLES (the reference raises RuntimeError). */
+NOMAD_B200_API size_t nomad_b200_embed_workspace_bytes(const int64_t* sample_offsets, int B);
+NOMAD_B200_API int nomad_b200_embed(nomad_b200_handle* h, const float* wav_dev, const int64_t* sample_offsets, int B,
+                     float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Same, HOST buffers in and out (pinned or pageable); H2D + compute + D2H + stream sync inside. */
+NOMAD_B200_API int nomad_b200_embed_host(nomad_b200_handle* h, const float* wav_host, const int64_t* sample_offsets, int B,
+                          float* emb_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- loss: ``Nomad.forward(estimate, clean)`` (nomad.py:142-146, 243-282) + its backward ---------
+ * est, clean: B x N fp32 device (the (B,1,N) tensors squeezed).  loss: 1 fp32 device.
+ * d_est: B x N fp32 device = d loss / d estimate (already including ``feature_grad_mult``), or NULL
+ * for forward only.  Weight gradients are not produced (wheel 0.0.8 semantics). */
+NOMAD_B200_API size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad);
+NOMAD_B200_API int nomad_b200_loss_fwd_bwd(nomad_b200_handle* h, const float* est_dev, const float* clean_dev, int B, int64_t N,
+                            float feature_grad_mult, float* loss_dev, float* d_est_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream);
+
+/* ``LossNetLayers.forward`` (nomad.py:243-258): the 12 layer outputs (12 x B x T x 768 fp32, layer
+ * major) and the head output (B x 256) for a fixed-length batch.  Either output may be NULL. */
+NOMAD_B200_API size_t nomad_b200_layers_workspace_bytes(int B, int64_t N);
+NOMAD_B200_API int64_t nomad_b200_num_frames(int64_t n_samples);
+NOMAD_B200_API int nomad_b200_layers_fwd(nomad_b200_handle* h, const float* wav_dev, int B, int64_t N, float* layers_dev,
+                          float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- distance: ``cdist(test, nmr)`` + ``np.mean(axis=1)`` (nomad.py:108,111) ---------------------
+ * deg: n x 256, nmr: m x 256 fp32 device.  dm (n x m fp32 device, may be NULL when only the means are
+ * wanted) and row_mean (n fp64 device).  No handle: the kernel has no weights. */
+NOMAD_B200_API size_t nomad_b200_cdist_workspace_bytes(int64_t n, int64_t m);
+NOMAD_B200_API int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev, int64_t m, float* dm_dev,
+                          double* row_mean_dev, void* workspace_dev, size_t workspace_bytes, int gemm_impl,
+                          void* stream);
+NOMAD_B200_API int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nmr_host, int64_t m, float* dm_host,
+                               double* row_mean_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- building block exposed for the parity tests --------------------------------------------------
+ * C (m x n, ldc) = epilogue(A (m x k bf16, row stride lda elements, may overlap) * B^T (n x k bf16)).
+ * flags: 1 bias, 2 GELU(erf), 4 + residual fp32 (ld = ldc), 8 store fp32 (c_f32), 16 store bf16 (c_bf16).
+ * a_rows = rows addressable in A's buffer; k_wrap as documented in DESIGN.md (0 = plain). */
+NOMAD_B200_API int nomad_b200_gemm_bf16(const void* a_bf16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_bf16, int m,
+                         int n, int k, int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride,
+                         const float* bias, const float* resid, float* c_f32, void* c_bf16, int64_t ldc, int flags,
+                         int gemm_impl, void* stream);
+
+/* Number of kernels this library has launched in this process (bench.py's ``gpu_launches``). */
+NOMAD_B200_API int64_t nomad_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOMAD_B200_H */

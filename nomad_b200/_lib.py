@@ -1,0 +1,76 @@
+"""ctypes binding of ``libnomad_b200.so`` (the C ABI declared in ``include/nomad_b200.h``).
+
+The product path has no CPU fallback: if the shared library is missing this module raises, it never
+routes around it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libnomad_b200.so")
+
+c_i64 = C.c_int64
+c_vp = C.c_void_p
+
+
+class Tensor(C.Structure):
+    """``nomad_b200_tensor``"""
+    _fields_ = [("name", C.c_char_p), ("data", c_vp), ("numel", c_i64)]
+
+
+# name -> (restype, argtypes): mirrors include/nomad_b200.h one to one
+PROTOTYPES = {
+    "nomad_b200_last_error": (C.c_char_p, []),
+    "nomad_b200_version": (C.c_char_p, []),
+    "nomad_b200_create": (C.c_int, [C.POINTER(c_vp), C.POINTER(Tensor), C.c_int, C.c_int]),
+    "nomad_b200_destroy": (C.c_int, [c_vp]),
+    "nomad_b200_set_gemm_impl": (C.c_int, [c_vp, C.c_int]),
+    "nomad_b200_set_loss_head": (C.c_int, [c_vp, c_vp, c_vp]),
+    "nomad_b200_embed_workspace_bytes": (C.c_size_t, [C.POINTER(c_i64), C.c_int]),
+    "nomad_b200_embed": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_vp, C.c_size_t, c_vp]),
+    "nomad_b200_embed_host": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_vp, C.c_size_t, c_vp]),
+    "nomad_b200_loss_workspace_bytes": (C.c_size_t, [C.c_int, c_i64, C.c_int]),
+    "nomad_b200_loss_fwd_bwd": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_i64, C.c_float, c_vp, c_vp, c_vp,
+                                          C.c_size_t, c_vp]),
+    "nomad_b200_layers_workspace_bytes": (C.c_size_t, [C.c_int, c_i64]),
+    "nomad_b200_num_frames": (c_i64, [c_i64]),
+    "nomad_b200_layers_fwd": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
+    "nomad_b200_cdist_workspace_bytes": (C.c_size_t, [c_i64, c_i64]),
+    "nomad_b200_cdist_mean": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, C.c_int, c_vp]),
+    "nomad_b200_cdist_mean_host": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
+    "nomad_b200_gemm_bf16": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
+    "nomad_b200_launch_count": (c_i64, []),
+}
+
+_lib = None
+
+
+class NomadB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach prototypes.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NomadB200Error(
+            f"{LIB_PATH} not found: build it with `make -C nomad_b200/csrc` (or `python -c 'import "
+            f"__graft_entry__ as g; g.build()'`). nomad_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().nomad_b200_last_error().decode("utf-8", "replace")
+        raise NomadB200Error(f"{what or 'nomad_b200 call'} failed: {msg}")

@@ -1,0 +1,405 @@
+// bf16 x bf16 -> fp32 GEMM for sm_100a: TMA-staged operand tiles, tcgen05.mma with the accumulator
+// in TMEM, warp-specialised persistent CTAs (1 TMA warp, 1 MMA warp, 8 epilogue warps), double-buffered
+// accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// C[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] ),  A and B both K-major ("TN" GEMM: activations
+// x weight^T, which is what nn.Linear / conv-as-GEMM need).
+#include "gemm.cuh"
+
+#include <mutex>
+
+namespace nb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+template <int BN>
+struct TileCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+    int M, N, K, batch;
+    int umma_n;  // N of the MMA instruction (<= BN, multiple of 16)
+    int m_tiles, n_tiles;
+    int a_wrap;  // GemmOperand::k_wrap of A
+    GemmEpilogue epi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for one (row, 32-column chunk): v[] holds the fp32 accumulators.
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, int col0,
+                                               int ncols, int b) {
+    const int flags = e.flags;
+    if (flags & EPI_BIAS) {
+        const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bstride + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j * 4 < ncols) {
+                const float4 t = __ldg(bp + j);
+                v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+        }
+    }
+    if (flags & EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
+    if (flags & EPI_MUL_AUX) {
+        const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j * 8 < ncols) {
+                const uint4 t = __ldg(ap + j);
+                float2 f;
+                f = unpack_bf16(t.x); v[8 * j + 0] *= f.x; v[8 * j + 1] *= f.y;
+                f = unpack_bf16(t.y); v[8 * j + 2] *= f.x; v[8 * j + 3] *= f.y;
+                f = unpack_bf16(t.z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
+                f = unpack_bf16(t.w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
+            }
+        }
+    }
+    if (flags & EPI_RESID) {
+        const float4* rp =
+            reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0 + (long long)b * e.resid_bstride);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j * 4 < ncols) {
+                const float4 t = __ldg(rp + j);
+                v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+        }
+    }
+    if (flags & EPI_OUT_F32) {
+        float4* op = reinterpret_cast<float4*>(e.out_f + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j * 4 < ncols) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (flags & EPI_OUT_BF16) {
+        uint4* op = reinterpret_cast<uint4*>(e.out_h + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j * 8 < ncols)
+                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+}
+
+// Scalar twin of the above (SIMT check kernel).
+__device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, long long row, int col, int b) {
+    const int flags = e.flags;
+    if (flags & EPI_CDIST) {
+        const float d2 = e.norm_a[row] + e.norm_b[col] - 2.0f * v;
+        const float d = sqrtf(fmaxf(d2, 0.0f));
+        if (e.out_f) e.out_f[row * e.ldo + col] = d;
+        atomicAdd(e.row_sum + row, (double)d);
+        return;
+    }
+    if (flags & EPI_BIAS) v += e.bias[(long long)b * e.bias_bstride + col];
+    if (flags & EPI_GELU) v = gelu_erf(v);
+    const long long off = row * e.ldo + col + (long long)b * e.out_bstride;
+    if (flags & EPI_MUL_AUX) v *= __bfloat162float(e.aux[off]);
+    if (flags & EPI_RESID) v += e.resid[row * e.ldr + col + (long long)b * e.resid_bstride];
+    if (flags & EPI_OUT_F32) e.out_f[off] = v;
+    if (flags & EPI_OUT_BF16) e.out_h[off] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+    using Cfg = TileCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.m_tiles * args.n_tiles * args.batch;
+    const int k_blocks = (args.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = Cfg::A_BYTES + (uint32_t)args.umma_n * BK * 2;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_blk = tile % args.n_tiles;
+                const int m_blk = (tile / args.n_tiles) % args.m_tiles;
+                const int b = tile / (args.n_tiles * args.m_tiles);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    if (args.a_wrap > 0) {
+                        const int kk = kb * BK;
+                        tma_load_3d(sa, &tmA, &full_bar[stage], kk % args.a_wrap, m_blk * BM + kk / args.a_wrap, b);
+                    } else {
+                        tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, b);
+                    }
+                    tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN, b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BM, args.umma_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int ew = warp - 4;
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int h = ew >> 2;           // column half
+        constexpr int HALF = BN / 2;
+        constexpr int CHUNKS = (HALF + 31) / 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int n_blk = tile % args.n_tiles;
+            const int m_blk = (tile / args.n_tiles) % args.m_tiles;
+            const int b = tile / (args.n_tiles * args.m_tiles);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * BM + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int ccol = h * HALF + c * 32;  // column inside the tile
+                const int col0 = n_blk * BN + ccol;
+                int ncols = args.N - col0;
+                ncols = ncols > 32 ? 32 : ncols;
+                if (ccol >= args.umma_n) ncols = 0;
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + ccol) + ((uint32_t)(q * 32) << 16), r);
+                tmem_ld_wait();
+                if (row < args.M && ncols > 0) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    epilogue_chunk(args.epi, v, row, col0, ncols, b);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT check kernel: same operands, same epilogue, one thread per output element.  Used by the GPU
+// parity tests to cross-check the tensor-core kernel on device (and selectable with
+// NOMAD_B200_GEMM=simt for debugging); never the default.
+__global__ void gemm_simt_kernel(GemmOperand A, GemmOperand B, GemmArgs args) {
+    __shared__ float sa[16][17];
+    __shared__ float sb[16][17];
+    const int b = blockIdx.z;
+    const long long row = (long long)blockIdx.y * 16 + threadIdx.y;
+    const int col = blockIdx.x * 16 + threadIdx.x;
+    const bf16* a = A.ptr + (long long)b * A.batch_stride;
+    const bf16* w = B.ptr + (long long)b * B.batch_stride;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < args.K; k0 += 16) {
+        const long long ar = (long long)blockIdx.y * 16 + threadIdx.y;
+        const int ak = k0 + threadIdx.x;
+        const long long aoff = A.k_wrap > 0 ? (ar + ak / A.k_wrap) * A.row_stride + ak % A.k_wrap : ar * A.row_stride + ak;
+        sa[threadIdx.y][threadIdx.x] = (ar < args.M && ak < args.K) ? __bfloat162float(a[aoff]) : 0.f;
+        const int br = blockIdx.x * 16 + threadIdx.y;
+        sb[threadIdx.y][threadIdx.x] = (br < args.N && ak < args.K) ? __bfloat162float(w[(long long)br * B.row_stride + ak]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fmaf(sa[threadIdx.y][k], sb[threadIdx.x][k], acc);
+        __syncthreads();
+    }
+    if (row < args.M && col < args.N) epilogue_scalar(args.epi, acc, row, col, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 3-D map over (K, rows, batch) of a bf16 operand, box = (64, box_rows, 1), 128-byte swizzle.
+static int make_operand_map(CUtensorMap* map, const GemmOperand& op, int K, int batch, int box_rows) {
+    if (op.k_wrap > 0) {
+        NB_CHECK(op.k_wrap % BK == 0 && op.row_stride == op.k_wrap, "wrapped-K operand needs k_wrap %% 64 == 0 and row_stride == k_wrap");
+        K = op.k_wrap;
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    NB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    NB_CHECK((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+    NB_CHECK((op.row_stride * 2) % 16 == 0 && (op.batch_stride * 2) % 16 == 0,
+             "GEMM operand strides must be multiples of 16 bytes (row_stride=%lld batch_stride=%lld)", op.row_stride,
+             op.batch_stride);
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)op.rows, (cuuint64_t)batch};
+    cuuint64_t gstride[2] = {(cuuint64_t)op.row_stride * 2,
+                             (cuuint64_t)(batch > 1 ? op.batch_stride : op.row_stride * op.rows) * 2};
+    if (gstride[1] == 0) gstride[1] = 16;
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(op.ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NB_CHECK(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled failed (%d): K=%d rows=%lld batch=%d row_stride=%lld batch_stride=%lld box_rows=%d",
+             (int)r, K, op.rows, batch, op.row_stride, op.batch_stride, box_rows);
+    return 0;
+}
+
+int device_sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+
+template <int BN>
+static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    using Cfg = TileCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
+    NB_TRY(make_operand_map(&tmB, B, args.K, args.batch, args.umma_n));
+    args.m_tiles = (args.M + BM - 1) / BM;
+    args.n_tiles = (args.N + BN - 1) / BN;
+    const long long tiles = (long long)args.m_tiles * args.n_tiles * args.batch;
+    int grid = device_sm_count();
+    if (tiles < grid) grid = (int)tiles;
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
+    NB_LAUNCHED();
+    return 0;
+}
+
+int gemm_bf16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
+              const GemmEpilogue& epi, int impl) {
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    NB_CHECK(K > 0 && K % 8 == 0, "GEMM K=%d must be a positive multiple of 8", K);
+    GemmArgs args;
+    args.M = M; args.N = N; args.K = K; args.batch = batch;
+    args.epi = epi;
+    args.umma_n = 0; args.m_tiles = args.n_tiles = 0;
+    args.a_wrap = A.k_wrap;
+    NB_CHECK(B.k_wrap == 0, "only the A operand may use wrapped K");
+    if (!(epi.flags & EPI_CDIST)) {
+        NB_CHECK(N % 8 == 0 && epi.ldo % 8 == 0 && epi.out_bstride % 8 == 0,
+                 "GEMM epilogue needs N, ldo, out_bstride multiples of 8 (N=%d ldo=%lld bstride=%lld)", N, epi.ldo,
+                 epi.out_bstride);
+        NB_CHECK(!(epi.flags & EPI_RESID) || (epi.ldr % 4 == 0 && epi.resid_bstride % 4 == 0),
+                 "GEMM residual leading dimension must be a multiple of 4");
+    }
+    if (impl == 1 || (epi.flags & EPI_CDIST)) {
+        dim3 grid((N + 15) / 16, (M + 15) / 16, batch), block(16, 16);
+        gemm_simt_kernel<<<grid, block, 0, st>>>(A, B, args);
+        NB_LAUNCHED();
+        return 0;
+    }
+    if (N > 128) {
+        args.umma_n = 256;
+        return launch_tc<256>(st, A, B, args);
+    } else if (N > 64) {
+        args.umma_n = 128;
+        return launch_tc<128>(st, A, B, args);
+    } else {
+        args.umma_n = (N + 15) / 16 * 16;
+        return launch_tc<64>(st, A, B, args);
+    }
+}
+
+}  // namespace nb
