@@ -58,7 +58,7 @@ NOMAD_B200_API const char* nomad_b200_last_error(void);
 NOMAD_B200_API const char* nomad_b200_version(void);
 
 /* Replaces model construction + ``load_state_dict`` (nomad.py:53-68).  Folds weight-norm, permutes
- * conv weights to K-major, fuses q/k/v, converts to bf16 and uploads to ``device``. */
+ * conv weights to K-major, fuses q/k/v, converts to op_t and uploads to ``device``. */
 NOMAD_B200_API int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors, int device);
 NOMAD_B200_API int nomad_b200_destroy(nomad_b200_handle* h);
 NOMAD_B200_API int nomad_b200_set_gemm_impl(nomad_b200_handle* h, int gemm_impl);
@@ -108,12 +108,12 @@ NOMAD_B200_API int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, 
                                double* row_mean_host, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- building block exposed for the parity tests --------------------------------------------------
- * C (m x n, ldc) = epilogue(A (m x k bf16, row stride lda elements, may overlap) * B^T (n x k bf16)).
- * flags: 1 bias, 2 GELU(erf), 4 + residual fp32 (ld = ldc), 8 store fp32 (c_f32), 16 store bf16 (c_bf16).
+ * C (m x n, ldc) = epilogue(A (m x k op_t, row stride lda elements, may overlap) * B^T (n x k op_t)).
+ * flags: 1 bias, 2 GELU(erf), 4 + residual fp32 (ld = ldc), 8 store fp32 (c_f32), 16 store op_t (c_f16).
  * a_rows = rows addressable in A's buffer; k_wrap as documented in DESIGN.md (0 = plain). */
-NOMAD_B200_API int nomad_b200_gemm_bf16(const void* a_bf16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_bf16, int m,
+NOMAD_B200_API int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_f16, int m,
                          int n, int k, int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride,
-                         const float* bias, const float* resid, float* c_f32, void* c_bf16, int64_t ldc, int flags,
+                         const float* bias, const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags,
                          int gemm_impl, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's ``gpu_launches``). */

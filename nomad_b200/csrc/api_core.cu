@@ -28,25 +28,25 @@ const char* nomad_b200_last_error(void) { return nb::get_error(); }
 const char* nomad_b200_version(void) { return "nomad_b200 0.1 (sm_100a)"; }
 int64_t nomad_b200_launch_count(void) { return nb::g_launches.load(); }
 
-int nomad_b200_gemm_bf16(const void* a_bf16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_bf16, int m, int n,
+int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_f16, int m, int n,
                          int k, int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride, const float* bias,
-                         const float* resid, float* c_f32, void* c_bf16, int64_t ldc, int flags, int gemm_impl,
+                         const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags, int gemm_impl,
                          void* stream) {
-    nb::GemmOperand A{(const nb::bf16*)a_bf16, a_rows, lda, a_bstride, k_wrap};
-    nb::GemmOperand B{(const nb::bf16*)b_bf16, n, k, b_bstride, 0};
+    nb::GemmOperand A{(const nb::op_t*)a_f16, a_rows, lda, a_bstride, k_wrap};
+    nb::GemmOperand B{(const nb::op_t*)b_f16, n, k, b_bstride, 0};
     nb::GemmEpilogue e;
     memset(&e, 0, sizeof(e));
-    e.flags = flags & (nb::EPI_BIAS | nb::EPI_GELU | nb::EPI_RESID | nb::EPI_OUT_F32 | nb::EPI_OUT_BF16);
+    e.flags = flags & (nb::EPI_BIAS | nb::EPI_GELU | nb::EPI_RESID | nb::EPI_OUT_F32 | nb::EPI_OUT_H16);
     e.bias = bias;
     e.bias_bstride = n;
     e.resid = resid;
     e.ldr = ldc;
     e.resid_bstride = c_bstride;
     e.out_f = c_f32;
-    e.out_h = (nb::bf16*)c_bf16;
+    e.out_h = (nb::op_t*)c_f16;
     e.ldo = ldc;
     e.out_bstride = c_bstride;
-    return nb::gemm_bf16((cudaStream_t)stream, A, B, m, n, k, batch, e, gemm_impl);
+    return nb::gemm_h16((cudaStream_t)stream, A, B, m, n, k, batch, e, gemm_impl);
 }
 
 }  // extern "C"

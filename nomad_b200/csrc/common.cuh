@@ -2,14 +2,24 @@
 // PTX wrappers for mbarrier, TMA (cp.async.bulk.tensor) and tcgen05 (UMMA + TMEM).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace nb {
 
-typedef __nv_bfloat16 bf16;
+// 16-bit tensor-core operand type.  fp16 (11-bit significand) rather than bf16 (8-bit): same tcgen05
+// kind::f16 rate, 8x less rounding noise -- that is what brings embeddings within 1e-3 of the fp32
+// reference (bf16 operands measured 2-3e-3, profiles/r01_parity_probe_bf16.log).  The residual stream,
+// all normalisation statistics, softmax and the accumulators stay fp32; conversions saturate.
+typedef __half op_t;
+static constexpr float OP_MAX = 65504.0f;
+__host__ __device__ __forceinline__ op_t f2op(float v) {
+    v = v > OP_MAX ? OP_MAX : (v < -OP_MAX ? -OP_MAX : v);
+    return __float2half_rn(v);
+}
+__host__ __device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
 
 // ---------------------------------------------------------------- error handling (host)
 void set_error(const char* fmt, ...);
@@ -59,8 +69,22 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ float gelu_erf(float x) {
+__device__ __forceinline__ float gelu_erf_exact(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~10 FMA instead of
+// libdevice erff's ~30 instructions.  gelu(x) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float e = fmaf(-p, __expf(-z * z), 1.0f);
+    return fmaf(0.5f * ax, e, 0.5f * x);
 }
 // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
@@ -78,13 +102,15 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -OP_MAX), OP_MAX);
+    hi = fminf(fmaxf(hi, -OP_MAX), OP_MAX);
+    __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_op(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -149,7 +175,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16/fp16 operands with fp32 accumulate.
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16/bf16 operands with fp32 accumulate.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
     asm volatile(
@@ -169,9 +195,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: fp16 x fp16 (a/b format 0) -> fp32 (c format 1), both operands K-major.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_h16(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i of this warp's quarter).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -1,0 +1,101 @@
+// Pairwise Euclidean distance + row mean:  scipy.spatial.distance.cdist(test, nmr) followed by
+// np.mean(axis=1) (reference nomad.py:108,111).
+//
+// fp32 direct-difference kernel: d = sqrt(sum_k (a_k - b_k)^2).  The direct form has no cancellation
+// (unit-norm embeddings give distances down to ~0.1 where the Gram form ||a||^2 + ||b||^2 - 2ab loses
+// 3-4 digits), so it meets the 1e-5 bound against scipy's float64 result without tricks.  Row sums are
+// accumulated in fp64.
+#include "kernels.cuh"
+
+namespace nb {
+
+static constexpr int CD_TILE = 64, CD_K = 32, CD_DIM = 256;
+
+__global__ void __launch_bounds__(256) cdist_fp32_kernel(const float* __restrict__ a, long long n,
+                                                         const float* __restrict__ b, long long m,
+                                                         float* __restrict__ dm, double* __restrict__ row_sum) {
+    __shared__ __align__(16) float As[CD_K][CD_TILE + 4];
+    __shared__ __align__(16) float Bs[CD_K][CD_TILE + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long row0 = (long long)blockIdx.y * CD_TILE, col0 = (long long)blockIdx.x * CD_TILE;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < CD_DIM; k0 += CD_K) {
+        // 64 rows x 32 k per operand = 512 float4 loads; 256 threads x 2
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int idx = threadIdx.x + it * 256;
+            const int r = idx >> 3, kq = (idx & 7) * 4;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (row0 + r < n) va = __ldg(reinterpret_cast<const float4*>(a + (row0 + r) * CD_DIM + k0 + kq));
+            if (col0 + r < m) vb = __ldg(reinterpret_cast<const float4*>(b + (col0 + r) * CD_DIM + k0 + kq));
+            As[kq + 0][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
+            Bs[kq + 0][r] = vb.x; Bs[kq + 1][r] = vb.y; Bs[kq + 2][r] = vb.z; Bs[kq + 3][r] = vb.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CD_K; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w};
+            const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = ar[i] - br[j];
+                    acc[i][j] = fmaf(d, d, acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long row = row0 + ty * 4 + i;
+        float d[4];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            d[j] = sqrtf(acc[i][j]);
+            if (col0 + tx * 4 + j < m) s += (double)d[j];
+        }
+        // reduce the 16 column-threads of this row (they are 16 consecutive lanes)
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row < n) {
+            if (dm != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long col = col0 + tx * 4 + j;
+                    if (col < m) dm[row * m + col] = d[j];
+                }
+            }
+            if (tx == 0) atomicAdd(row_sum + row, s);
+        }
+    }
+}
+
+__global__ void scale_rows_kernel(double* v, long long n, double s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= s;
+}
+
+int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
+                      double* row_mean) {
+    if (n <= 0) return 0;
+    NB_CUDA(cudaMemsetAsync(row_mean, 0, sizeof(double) * n, st));
+    if (m <= 0) return 0;
+    dim3 grid((unsigned)((m + CD_TILE - 1) / CD_TILE), (unsigned)((n + CD_TILE - 1) / CD_TILE));
+    NB_CHECK(grid.y <= 65535u, "cdist: too many rows for one launch (%lld); chunk the call", n);
+    cdist_fp32_kernel<<<grid, 256, 0, st>>>(a, n, b, m, dm, row_mean);
+    NB_LAUNCHED();
+    scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_mean, n, 1.0 / (double)m);
+    NB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace nb

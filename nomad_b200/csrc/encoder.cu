@@ -1,0 +1,395 @@
+// Transformer-side kernels that are not GEMMs: positional-conv staging, LayerNorm(768) with residual
+// stream bookkeeping, the attention core and the pooled embedding head.
+#include "kernels.cuh"
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+// Positional conv staging.  The grouped conv (768 ch, 16 groups, k = 128, pad 64) becomes 16 GEMMs
+// with overlapping rows once every group's 48 channels are contiguous per frame and every utterance
+// is surrounded by >= 64 zero frames:  pos_g[g][p][c], p = pos0(utt) + t.  Row m of the GEMM's A
+// operand is then the 128 x 48 window starting at p = m, i.e. output frame p = m + 64.
+// The buffer is zero-filled beforehand; this kernel scatters the valid frames.
+__global__ void __launch_bounds__(384) pos_scatter_kernel(const float* __restrict__ x,
+                                                          const UttMeta* __restrict__ meta, int B, long long frames,
+                                                          long long pos_rows_alloc, op_t* __restrict__ pos_g) {
+    const long long f = (long long)blockIdx.x * 4 + threadIdx.x / 96;
+    if (f >= frames) return;
+    const int i = threadIdx.x % 96;  // 8-channel chunk
+    const int b = find_utt_by_frame(meta, B, (int)f);
+    const int t = (int)f - meta[b].frame0;
+    if (t >= meta[b].T) return;
+    const long long p = meta[b].pos0 + t;
+    const float4* src = reinterpret_cast<const float4*>(x + f * EMBED + i * 8);
+    const float4 a = __ldg(src), c = __ldg(src + 1);
+    const int ch = i * 8, g = ch / POS_GC, cc = ch % POS_GC;
+    uint4* dst = reinterpret_cast<uint4*>(pos_g + ((long long)g * pos_rows_alloc + p) * POS_GC + cc);
+    *dst = make_uint4(pack_op(a.x, a.y), pack_op(a.z, a.w), pack_op(c.x, c.y), pack_op(c.z, c.w));
+}
+
+int launch_pos_scatter(cudaStream_t st, const float* x, const UttMeta* meta, int B, long long frames,
+                       long long pos_rows_alloc, op_t* pos_g) {
+    pos_scatter_kernel<<<(unsigned)((frames + 3) / 4), 384, 0, st>>>(x, meta, B, frames, pos_rows_alloc, pos_g);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm(768), one warp per frame; lane owns the 8-channel chunks {lane, lane + 32, lane + 64}.
+struct Row768 {
+    float v[24];
+};
+
+__device__ __forceinline__ void ln768_normalise(Row768& r, const float* __restrict__ g, const float* __restrict__ bta,
+                                                int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s += r.v[i];
+    const float mean = warp_sum(s) * (1.0f / EMBED);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { const float d = r.v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / EMBED) + 1e-5f);
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bta + c0 + 4));
+        float* v = r.v + 8 * h;
+        v[0] = (v[0] - mean) * rstd * g0.x + b0.x; v[1] = (v[1] - mean) * rstd * g0.y + b0.y;
+        v[2] = (v[2] - mean) * rstd * g0.z + b0.z; v[3] = (v[3] - mean) * rstd * g0.w + b0.w;
+        v[4] = (v[4] - mean) * rstd * g1.x + b1.x; v[5] = (v[5] - mean) * rstd * g1.y + b1.y;
+        v[6] = (v[6] - mean) * rstd * g1.z + b1.z; v[7] = (v[7] - mean) * rstd * g1.w + b1.w;
+    }
+}
+
+__device__ __forceinline__ void row768_store(const Row768& r, long long f, int lane, float* __restrict__ x,
+                                             op_t* __restrict__ xh) {
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        const float* v = r.v + 8 * h;
+        float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
+        xo[0] = make_float4(v[0], v[1], v[2], v[3]);
+        xo[1] = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<uint4*>(xh + f * EMBED + c0) =
+            make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+    }
+}
+
+__device__ __forceinline__ void row768_store_zero(long long f, int lane, float* __restrict__ x, op_t* __restrict__ xh) {
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
+        xo[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xo[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<uint4*>(xh + f * EMBED + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// x = LN(x0 + GELU(posconv)) (the GELU'd conv is pos_y, op_t, in the padded row layout)
+__global__ void __launch_bounds__(256) pos_finish_ln_kernel(const float* __restrict__ x0, const op_t* __restrict__ pos_y,
+                                                            const UttMeta* __restrict__ meta, int B, long long frames,
+                                                            const float* __restrict__ g, const float* __restrict__ bta,
+                                                            float* __restrict__ x, op_t* __restrict__ xh) {
+    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (f >= frames) return;
+    const int lane = threadIdx.x & 31;
+    const int b = find_utt_by_frame(meta, B, (int)f);
+    const int t = (int)f - meta[b].frame0;
+    if (t >= meta[b].T) {
+        row768_store_zero(f, lane, x, xh);
+        return;
+    }
+    const long long m = (long long)meta[b].pos0 + t - POS_K / 2;
+    Row768 r;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        const float4* xp = reinterpret_cast<const float4*>(x0 + f * EMBED + c0);
+        const float4 a = __ldg(xp), c = __ldg(xp + 1);
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(pos_y + m * EMBED + c0));
+        float2 y0 = unpack_op(y.x), y1 = unpack_op(y.y), y2 = unpack_op(y.z), y3 = unpack_op(y.w);
+        float* v = r.v + 8 * h;
+        v[0] = a.x + y0.x; v[1] = a.y + y0.y; v[2] = a.z + y1.x; v[3] = a.w + y1.y;
+        v[4] = c.x + y2.x; v[5] = c.y + y2.y; v[6] = c.z + y3.x; v[7] = c.w + y3.y;
+    }
+    ln768_normalise(r, g, bta, lane);
+    row768_store(r, f, lane, x, xh);
+}
+
+int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, const UttMeta* meta, int B,
+                         long long frames, const float* g, const float* b, float* x, op_t* xh) {
+    pos_finish_ln_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(x0, pos_y, meta, B, frames, g, b, x, xh);
+    NB_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) ln768_kernel(const float* __restrict__ pre, const UttMeta* __restrict__ meta,
+                                                    int B, long long frames, const float* __restrict__ g,
+                                                    const float* __restrict__ bta, float* __restrict__ x,
+                                                    op_t* __restrict__ xh, float* __restrict__ layer_out, int layer_T) {
+    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (f >= frames) return;
+    const int lane = threadIdx.x & 31;
+    const int b = find_utt_by_frame(meta, B, (int)f);
+    const int t = (int)f - meta[b].frame0;
+    if (t >= meta[b].T) {
+        row768_store_zero(f, lane, x, xh);
+        return;
+    }
+    Row768 r;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        const float4* xp = reinterpret_cast<const float4*>(pre + f * EMBED + c0);
+        const float4 a = __ldg(xp), c = __ldg(xp + 1);
+        float* v = r.v + 8 * h;
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    }
+    ln768_normalise(r, g, bta, lane);
+    row768_store(r, f, lane, x, xh);
+    if (layer_out != nullptr) {
+        float* lo = layer_out + ((long long)b * layer_T + t) * EMBED;
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            const int c0 = (lane + 32 * h) * 8;
+            const float* v = r.v + 8 * h;
+            float4* o = reinterpret_cast<float4*>(lo + c0);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+}
+
+int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
+                 const float* b, float* x, op_t* xh, float* layer_out, int layer_T) {
+    ln768_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(pre, meta, B, frames, g, b, x, xh, layer_out, layer_T);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention core: softmax(Q K^T) V per (utterance, head), non-causal, keys >= T masked.  q is already
+// scaled by head_dim^-0.5 (folded into the QKV weights).  Flash-style streaming over 64-key tiles with
+// online softmax; one CTA = 64 queries (4 warps x 16 rows), op_t mma.sync m16n8k16 with fp32 accumulate.
+// (T <= ~1000 frames here, so this is 3-12 % of the FLOPs; the GEMMs carry the rest.)
+static constexpr int ATT_BQ = 64, ATT_BK = 64;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_h16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 64 x 64 op_t tile, rows of 128 B, 16-byte chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ op_t* tile_ptr(op_t* base, int row, int col) {
+    return base + row * 64 + ((((col >> 3) ^ (row & 7)) << 3) | (col & 7));
+}
+
+// rows [row0, row0 + 64) of a (frames x 2304) matrix slice starting at column col0 -> swizzled tile
+__device__ __forceinline__ void load_tile_async(op_t* tile, const op_t* __restrict__ src, long long first_row,
+                                                int row0, int last_valid, int col0, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * 128;
+        const int r = idx >> 3, ch = idx & 7;
+        int gr = row0 + r;
+        gr = gr > last_valid ? last_valid : gr;  // clamp: padded rows replay a valid (finite) row
+        cp_async16(tile_ptr(tile, r, ch * 8), src + (first_row + gr) * (3 * EMBED) + col0 + ch * 8);
+    }
+}
+
+__global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__ qkv, const UttMeta* __restrict__ meta,
+                                                        op_t* __restrict__ out) {
+    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    const int T = meta[b].T;
+    const int q0 = qt * ATT_BQ;
+    if (q0 >= T) return;
+    const long long f0 = meta[b].frame0;
+    __shared__ __align__(128) op_t Qs[ATT_BQ * 64];
+    __shared__ __align__(128) op_t Ks[2][ATT_BK * 64];
+    __shared__ __align__(128) op_t Vs[2][ATT_BK * 64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (T + ATT_BK - 1) / ATT_BK;
+
+    load_tile_async(Qs, qkv, f0, q0, T - 1, h * HEAD_DIM, tid);
+    load_tile_async(Ks[0], qkv, f0, 0, T - 1, EMBED + h * HEAD_DIM, tid);
+    load_tile_async(Vs[0], qkv, f0, 0, T - 1, 2 * EMBED + h * HEAD_DIM, tid);
+    cp_async_commit();
+
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    uint32_t qf[4][4];
+    const float LOG2E = 1.4426950408889634f;
+
+    for (int kt = 0; kt < n_tiles; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_tiles) {
+            load_tile_async(Ks[buf ^ 1], qkv, f0, (kt + 1) * ATT_BK, T - 1, EMBED + h * HEAD_DIM, tid);
+            load_tile_async(Vs[buf ^ 1], qkv, f0, (kt + 1) * ATT_BK, T - 1, 2 * EMBED + h * HEAD_DIM, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (kt == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                ldsm_x4(qf[kk], tile_ptr(Qs, warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 16 + (lane >> 4) * 8));
+        }
+        // S = Q K^T : 16 x 64 per warp
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t kf[4];
+                ldsm_x4(kf, tile_ptr(Ks[buf], np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 16 + ((lane >> 3) & 1) * 8));
+                mma_h16(s[2 * np], qf[kk], kf[0], kf[1]);
+                mma_h16(s[2 * np + 1], qf[kk], kf[2], kf[3]);
+            }
+        }
+        // mask keys beyond T (only the last tile can have any)
+        const int key_base = kt * ATT_BK + 2 * (lane & 3);
+        if (kt == n_tiles - 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k0 = key_base + i * 8;
+                if (k0 >= T) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+                if (k0 + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+            }
+        }
+        // online softmax (rows lane/4 and lane/4 + 8)
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+        float scale[2], mnew[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mnew[r] = fmaxf(m_run[r], mx[r]);
+            scale[r] = exp2f((m_run[r] - mnew[r]) * LOG2E);
+            m_run[r] = mnew[r];
+            l_run[r] *= scale[r];
+        }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p0 = exp2f((s[i][0] - mnew[0]) * LOG2E), p1 = exp2f((s[i][1] - mnew[0]) * LOG2E);
+            const float p2 = exp2f((s[i][2] - mnew[1]) * LOG2E), p3 = exp2f((s[i][3] - mnew[1]) * LOG2E);
+            l_run[0] += p0 + p1;
+            l_run[1] += p2 + p3;
+            pf[i >> 1][(i & 1) * 2 + 0] = pack_op(p0, p1);
+            pf[i >> 1][(i & 1) * 2 + 1] = pack_op(p2, p3);
+            o[i][0] *= scale[0]; o[i][1] *= scale[0]; o[i][2] *= scale[1]; o[i][3] *= scale[1];
+        }
+        // O += P V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t vf[4];
+                ldsm_x4_t(vf, tile_ptr(Vs[buf], kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
+                mma_h16(o[2 * np], pf[kk], vf[0], vf[1]);
+                mma_h16(o[2 * np + 1], pf[kk], vf[2], vf[3]);
+            }
+        }
+        __syncthreads();  // everyone done with buf before it is refilled two iterations later
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    op_t* ob = out + f0 * EMBED + h * HEAD_DIM + 2 * (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * EMBED + i * 8) = pack_op(o[i][0] * inv0, o[i][1] * inv0);
+        if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * EMBED + i * 8) = pack_op(o[i][2] * inv1, o[i][3] * inv1);
+    }
+}
+
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out) {
+    dim3 grid((max_T + ATT_BQ - 1) / ATT_BQ, HEADS, B);
+    attention_kernel<<<grid, 128, 0, st>>>(qkv, meta, out);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean over the valid frames -> ReLU -> Linear(768, 256) -> L2 normalise  (nomad.py:228-230)
+__global__ void __launch_bounds__(256) pool_head_kernel(const float* __restrict__ x, const UttMeta* __restrict__ meta,
+                                                        const float* __restrict__ head_wt, const float* __restrict__ head_b,
+                                                        float* __restrict__ emb, float* __restrict__ pooled_out) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const UttMeta m = meta[b];
+    __shared__ float pooled[EMBED];
+    __shared__ float red[8];
+    const float* xp = x + (long long)m.frame0 * EMBED;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int t = 0; t < m.T; ++t) {
+        a0 += xp[(long long)t * EMBED + tid];
+        a1 += xp[(long long)t * EMBED + tid + 256];
+        a2 += xp[(long long)t * EMBED + tid + 512];
+    }
+    const float inv = 1.0f / (float)m.T;
+    a0 *= inv; a1 *= inv; a2 *= inv;
+    if (pooled_out != nullptr) {
+        pooled_out[(long long)b * EMBED + tid] = a0;
+        pooled_out[(long long)b * EMBED + tid + 256] = a1;
+        pooled_out[(long long)b * EMBED + tid + 512] = a2;
+    }
+    pooled[tid] = fmaxf(a0, 0.f);
+    pooled[tid + 256] = fmaxf(a1, 0.f);
+    pooled[tid + 512] = fmaxf(a2, 0.f);
+    __syncthreads();
+    float acc = head_b[tid];
+#pragma unroll 8
+    for (int k = 0; k < EMBED; ++k) acc = fmaf(pooled[k], __ldg(head_wt + k * EMB + tid), acc);
+    float sq = warp_sum(acc * acc);
+    if ((tid & 31) == 0) red[tid >> 5] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float denom = fmaxf(sqrtf(tot), 1e-12f);
+    emb[(long long)b * EMB + tid] = acc / denom;
+}
+
+int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
+                     const float* head_b, float* emb, float* pooled_out) {
+    pool_head_kernel<<<B, 256, 0, st>>>(x, meta, head_wt, head_b, emb, pooled_out);
+    NB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace nb

@@ -1,0 +1,223 @@
+// Front of the conv feature encoder: conv0 (1 -> 512, k = 10, s = 5) + GroupNorm(512 groups) + GELU,
+// and the LayerNorm(512) that follows the last conv.  All HBM-bound element-wise / reduction work.
+//
+// GroupNorm here normalises every (utterance, channel) over ALL conv0 frames of the utterance
+// (fairseq ConvFeatureExtractionModel mode "default"; mirror torchaudio components.py:564-569).  The
+// statistics of y[t, c] = sum_j w[c, j] x[5 t + j] are quadratic forms of the waveform's tap sums:
+//     sum_t y      = sum_j  w_j  S_j          S_j    = sum_t x[5 t + j]
+//     sum_t y^2    = sum_jj' w_j w_j' R_jj'    R_jj'  = sum_t x[5 t + j] x[5 t + j']
+// so one cheap pass over the waveform (65 sums per utterance, fp64) replaces a stats pass over the
+// 512-channel conv0 output, and normalisation folds into per-(utterance, channel) conv taps.
+#include "kernels.cuh"
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wav,
+                                                         const UttMeta* __restrict__ meta, int max_chunks,
+                                                         double* __restrict__ part) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const UttMeta m = meta[b];
+    const int t_begin = chunk * STAT_CHUNK;
+    if (t_begin >= m.T0) return;
+    const int t_end = min(m.T0, t_begin + STAT_CHUNK);
+    const float* x = wav + m.wav_off;
+    float acc[NSTAT];
+#pragma unroll
+    for (int i = 0; i < NSTAT; ++i) acc[i] = 0.f;
+    for (int t = t_begin + threadIdx.x; t < t_end; t += blockDim.x) {
+        float v[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) v[j] = __ldg(x + 5 * t + j);
+        int idx = 10;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            acc[j] += v[j];
+#pragma unroll
+            for (int k = j; k < 10; ++k) { acc[idx] = fmaf(v[j], v[k], acc[idx]); ++idx; }
+        }
+    }
+    __shared__ double red[8][NSTAT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NSTAT; ++i) {
+        double d = (double)acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) red[warp][i] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < NSTAT) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        part[((long long)b * max_chunks + chunk) * NSTAT + threadIdx.x] = s;
+    }
+}
+
+int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int B, int max_chunks, double* part) {
+    dim3 grid(max_chunks, B);
+    wave_stats_kernel<<<grid, 256, 0, st>>>(wav, meta, max_chunks, part);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold[b][c][0..9] = w[c][j] * rstd * gamma,  fold[b][c][10] = beta - mean * rstd * gamma
+__global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__ part,
+                                                      const UttMeta* __restrict__ meta, int max_chunks,
+                                                      const float* __restrict__ w0, const float* __restrict__ gn_g,
+                                                      const float* __restrict__ gn_b, float* __restrict__ fold) {
+    const int b = blockIdx.x;
+    const UttMeta m = meta[b];
+    __shared__ double s[NSTAT];
+    if (threadIdx.x < NSTAT) {
+        const int chunks = (m.T0 + STAT_CHUNK - 1) / STAT_CHUNK;
+        double a = 0.0;
+        for (int c = 0; c < chunks; ++c) a += part[((long long)b * max_chunks + c) * NSTAT + threadIdx.x];
+        s[threadIdx.x] = a;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    double w[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) w[j] = (double)w0[c * 10 + j];
+    double sum = 0.0, sq = 0.0;
+    int idx = 10;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        sum += w[j] * s[j];
+#pragma unroll
+        for (int k = j; k < 10; ++k) {
+            const double r = w[j] * w[k] * s[idx++];
+            sq += (k == j) ? r : 2.0 * r;
+        }
+    }
+    const double inv_n = 1.0 / (double)m.T0;
+    const double mean = sum * inv_n;
+    double var = sq * inv_n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double a = (double)gn_g[c] / sqrt(var + 1e-5);
+    float* o = fold + ((long long)b * CONV_DIM + c) * 12;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) o[j] = (float)(w[j] * a);
+    o[10] = (float)((double)gn_b[c] - mean * a);
+    o[11] = 0.f;
+}
+
+int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
+                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold) {
+    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One block = 64 consecutive level-0 rows (always inside one utterance: rows0 is a multiple of 64),
+// 256 threads x 2 channels.  out[row][c] = GELU(sum_j fold[c][j] x[5 t + j] + shift[c]) as op_t,
+// zeros for the padding rows t >= T0.
+static constexpr int C0_ROWS = 64;
+
+__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav,
+                                                          const UttMeta* __restrict__ meta, int B,
+                                                          const float* __restrict__ fold, op_t* __restrict__ out) {
+    const int row_base = blockIdx.x * C0_ROWS;
+    // utterance lookup: frame-level offsets are row offsets / 64
+    const int b = find_utt_by_frame(meta, B, blockIdx.x);
+    const UttMeta m = meta[b];
+    const int t_base = row_base - m.row0;
+    __shared__ float xs[C0_ROWS * 5 + 8];
+    const float* x = wav + m.wav_off;
+    for (int i = threadIdx.x; i < C0_ROWS * 5 + 5; i += blockDim.x) {
+        const long long s = (long long)t_base * 5 + i;
+        xs[i] = (s < m.n) ? __ldg(x + s) : 0.f;
+    }
+    const int c = 2 * threadIdx.x;
+    float w0[11], w1[11];
+    {
+        const float4* f = reinterpret_cast<const float4*>(fold + ((long long)b * CONV_DIM + c) * 12);
+        const float4 a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3), a4 = __ldg(f + 4),
+                     a5 = __ldg(f + 5);
+        w0[0] = a0.x; w0[1] = a0.y; w0[2] = a0.z; w0[3] = a0.w; w0[4] = a1.x; w0[5] = a1.y; w0[6] = a1.z;
+        w0[7] = a1.w; w0[8] = a2.x; w0[9] = a2.y; w0[10] = a2.z;
+        w1[0] = a3.x; w1[1] = a3.y; w1[2] = a3.z; w1[3] = a3.w; w1[4] = a4.x; w1[5] = a4.y; w1[6] = a4.z;
+        w1[7] = a4.w; w1[8] = a5.x; w1[9] = a5.y; w1[10] = a5.z;
+    }
+    __syncthreads();
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (long long)row_base * CONV_DIM + c);
+    const int valid = m.T0 - t_base;  // rows of this block that are real frames
+#pragma unroll 4
+    for (int t = 0; t < C0_ROWS; ++t) {
+        uint32_t packed = 0u;
+        if (t < valid) {
+            float y0 = w0[10], y1 = w1[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const float xv = xs[5 * t + j];
+                y0 = fmaf(w0[j], xv, y0);
+                y1 = fmaf(w1[j], xv, y1);
+            }
+            packed = pack_op(gelu_erf(y0), gelu_erf(y1));
+        }
+        o[(long long)t * (CONV_DIM / 2)] = packed;
+    }
+}
+
+int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
+                       const float* fold, op_t* out) {
+    conv0_apply_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, out);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over 512 channels, op_t in -> op_t out, one warp per row (16 values per lane).
+__global__ void __launch_bounds__(256) ln512_kernel(const op_t* __restrict__ in, long long rows,
+                                                    const float* __restrict__ g, const float* __restrict__ bta,
+                                                    op_t* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* p = reinterpret_cast<const uint4*>(in + row * CONV_DIM);
+    float v[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint4 u = __ldg(p + lane + 32 * h);
+        float2 f;
+        f = unpack_op(u.x); v[8 * h + 0] = f.x; v[8 * h + 1] = f.y;
+        f = unpack_op(u.y); v[8 * h + 2] = f.x; v[8 * h + 3] = f.y;
+        f = unpack_op(u.z); v[8 * h + 4] = f.x; v[8 * h + 5] = f.y;
+        f = unpack_op(u.w); v[8 * h + 6] = f.x; v[8 * h + 7] = f.y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / CONV_DIM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / CONV_DIM) + 1e-5f);
+    uint4* o = reinterpret_cast<uint4*>(out + row * CONV_DIM);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bta + c0 + 4));
+        float r[8];
+        r[0] = (v[8 * h + 0] - mean) * rstd * g0.x + b0.x; r[1] = (v[8 * h + 1] - mean) * rstd * g0.y + b0.y;
+        r[2] = (v[8 * h + 2] - mean) * rstd * g0.z + b0.z; r[3] = (v[8 * h + 3] - mean) * rstd * g0.w + b0.w;
+        r[4] = (v[8 * h + 4] - mean) * rstd * g1.x + b1.x; r[5] = (v[8 * h + 5] - mean) * rstd * g1.y + b1.y;
+        r[6] = (v[8 * h + 6] - mean) * rstd * g1.z + b1.z; r[7] = (v[8 * h + 7] - mean) * rstd * g1.w + b1.w;
+        o[lane + 32 * h] = make_uint4(pack_op(r[0], r[1]), pack_op(r[2], r[3]), pack_op(r[4], r[5]),
+                                      pack_op(r[6], r[7]));
+    }
+}
+
+int launch_ln512(cudaStream_t st, const op_t* in, long long rows, const float* g, const float* b, op_t* out) {
+    if (rows <= 0) return 0;
+    ln512_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, rows, g, b, out);
+    NB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace nb

@@ -1,4 +1,4 @@
-// bf16 x bf16 -> fp32 GEMM for sm_100a: TMA-staged operand tiles, tcgen05.mma with the accumulator
+// op_t x op_t -> fp32 GEMM for sm_100a: TMA-staged operand tiles, tcgen05.mma with the accumulator
 // in TMEM, warp-specialised persistent CTAs (1 TMA warp, 1 MMA warp, 8 epilogue warps), double-buffered
 // accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
 //
@@ -11,7 +11,7 @@
 namespace nb {
 
 static constexpr int BM = 128;
-static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+static constexpr int BK = 64;  // 64 op_t = 128 B = one swizzle-128B row
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
@@ -61,10 +61,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             if (j * 8 < ncols) {
                 const uint4 t = __ldg(ap + j);
                 float2 f;
-                f = unpack_bf16(t.x); v[8 * j + 0] *= f.x; v[8 * j + 1] *= f.y;
-                f = unpack_bf16(t.y); v[8 * j + 2] *= f.x; v[8 * j + 3] *= f.y;
-                f = unpack_bf16(t.z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
-                f = unpack_bf16(t.w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
+                f = unpack_op(t.x); v[8 * j + 0] *= f.x; v[8 * j + 1] *= f.y;
+                f = unpack_op(t.y); v[8 * j + 2] *= f.x; v[8 * j + 3] *= f.y;
+                f = unpack_op(t.z); v[8 * j + 4] *= f.x; v[8 * j + 5] *= f.y;
+                f = unpack_op(t.w); v[8 * j + 6] *= f.x; v[8 * j + 7] *= f.y;
             }
         }
     }
@@ -85,13 +85,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         for (int j = 0; j < 8; ++j)
             if (j * 4 < ncols) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
-    if (flags & EPI_OUT_BF16) {
+    if (flags & EPI_OUT_H16) {
         uint4* op = reinterpret_cast<uint4*>(e.out_h + off);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (j * 8 < ncols)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                op[j] = make_uint4(pack_op(v[8 * j], v[8 * j + 1]), pack_op(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_op(v[8 * j + 4], v[8 * j + 5]), pack_op(v[8 * j + 6], v[8 * j + 7]));
     }
 }
 
@@ -108,10 +108,10 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, 
     if (flags & EPI_BIAS) v += e.bias[(long long)b * e.bias_bstride + col];
     if (flags & EPI_GELU) v = gelu_erf(v);
     const long long off = row * e.ldo + col + (long long)b * e.out_bstride;
-    if (flags & EPI_MUL_AUX) v *= __bfloat162float(e.aux[off]);
+    if (flags & EPI_MUL_AUX) v *= op2f(e.aux[off]);
     if (flags & EPI_RESID) v += e.resid[row * e.ldr + col + (long long)b * e.resid_bstride];
     if (flags & EPI_OUT_F32) e.out_f[off] = v;
-    if (flags & EPI_OUT_BF16) e.out_h[off] = __float2bfloat16(v);
+    if (flags & EPI_OUT_H16) e.out_h[off] = f2op(v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BM, args.umma_n);
+            const uint32_t idesc = umma_idesc_h16(BM, args.umma_n);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -205,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        // advancing K by 16 op_t = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
                         umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
@@ -271,16 +271,16 @@ __global__ void gemm_simt_kernel(GemmOperand A, GemmOperand B, GemmArgs args) {
     const int b = blockIdx.z;
     const long long row = (long long)blockIdx.y * 16 + threadIdx.y;
     const int col = blockIdx.x * 16 + threadIdx.x;
-    const bf16* a = A.ptr + (long long)b * A.batch_stride;
-    const bf16* w = B.ptr + (long long)b * B.batch_stride;
+    const op_t* a = A.ptr + (long long)b * A.batch_stride;
+    const op_t* w = B.ptr + (long long)b * B.batch_stride;
     float acc = 0.f;
     for (int k0 = 0; k0 < args.K; k0 += 16) {
         const long long ar = (long long)blockIdx.y * 16 + threadIdx.y;
         const int ak = k0 + threadIdx.x;
         const long long aoff = A.k_wrap > 0 ? (ar + ak / A.k_wrap) * A.row_stride + ak % A.k_wrap : ar * A.row_stride + ak;
-        sa[threadIdx.y][threadIdx.x] = (ar < args.M && ak < args.K) ? __bfloat162float(a[aoff]) : 0.f;
+        sa[threadIdx.y][threadIdx.x] = (ar < args.M && ak < args.K) ? op2f(a[aoff]) : 0.f;
         const int br = blockIdx.x * 16 + threadIdx.y;
-        sb[threadIdx.y][threadIdx.x] = (br < args.N && ak < args.K) ? __bfloat162float(w[(long long)br * B.row_stride + ak]) : 0.f;
+        sb[threadIdx.y][threadIdx.x] = (br < args.N && ak < args.K) ? op2f(w[(long long)br * B.row_stride + ak]) : 0.f;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc = fmaf(sa[threadIdx.y][k], sb[threadIdx.x][k], acc);
@@ -307,7 +307,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D map over (K, rows, batch) of a bf16 operand, box = (64, box_rows, 1), 128-byte swizzle.
+// 3-D map over (K, rows, batch) of a op_t operand, box = (64, box_rows, 1), 128-byte swizzle.
 static int make_operand_map(CUtensorMap* map, const GemmOperand& op, int K, int batch, int box_rows) {
     if (op.k_wrap > 0) {
         NB_CHECK(op.k_wrap % BK == 0 && op.row_stride == op.k_wrap, "wrapped-K operand needs k_wrap %% 64 == 0 and row_stride == k_wrap");
@@ -325,7 +325,7 @@ static int make_operand_map(CUtensorMap* map, const GemmOperand& op, int K, int 
     if (gstride[1] == 0) gstride[1] = 16;
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(op.ptr), gdim, gstride, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<op_t*>(op.ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NB_CHECK(r == CUDA_SUCCESS,
@@ -367,7 +367,7 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     return 0;
 }
 
-int gemm_bf16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
+int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
     NB_CHECK(K > 0 && K % 8 == 0, "GEMM K=%d must be a positive multiple of 8", K);

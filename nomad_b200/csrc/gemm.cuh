@@ -1,6 +1,6 @@
-// Internal interface of the bf16 tensor-core GEMM used by every dense contraction of the path
+// Internal interface of the op_t tensor-core GEMM used by every dense contraction of the path
 // (conv layers 1-6 as overlapping-row implicit GEMMs, feature projection, grouped positional conv,
-// QKV / out-proj / FFN, their dgrad twins and the split-bf16 Gram matrix of the distance kernel).
+// QKV / out-proj / FFN, their dgrad twins and the split-op_t Gram matrix of the distance kernel).
 #pragma once
 #include "common.cuh"
 
@@ -11,17 +11,17 @@ enum : int {
     EPI_GELU = 2,      // exact erf GELU
     EPI_RESID = 4,     // + resid[row, col] (fp32)
     EPI_OUT_F32 = 8,   // store fp32
-    EPI_OUT_BF16 = 16, // store bf16
-    EPI_MUL_AUX = 32,  // * aux[row, col] (bf16)  -- dgrad through GELU: aux holds gelu'(pre-activation)
+    EPI_OUT_H16 = 16, // store op_t
+    EPI_MUL_AUX = 32,  // * aux[row, col] (op_t)  -- dgrad through GELU: aux holds gelu'(pre-activation)
     EPI_CDIST = 64,    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
 };
 
-// One operand: ``rows`` rows of K bf16 values, row r of batch b starting at
+// One operand: ``rows`` rows of K op_t values, row r of batch b starting at
 // ptr + b * batch_stride + r * row_stride (elements).  row_stride may be SMALLER than K
 // (overlapping rows): that is how a strided conv over a channels-last activation becomes a GEMM
 // without an im2col buffer.
 struct GemmOperand {
-    const bf16* ptr;
+    const op_t* ptr;
     long long rows;
     long long row_stride;
     long long batch_stride;
@@ -38,9 +38,9 @@ struct GemmEpilogue {
     const float* resid;       // fp32, element (row, col) at resid[row * ldr + col + b * resid_bstride]
     long long ldr;
     long long resid_bstride;
-    const bf16* aux;          // bf16, same indexing as out (ldo / out_bstride)
+    const op_t* aux;          // op_t, same indexing as out (ldo / out_bstride)
     float* out_f;             // element (row, col) of batch b at out[row * ldo + col + b * out_bstride]
-    bf16* out_h;
+    op_t* out_h;
     long long ldo;
     long long out_bstride;
     // EPI_CDIST
@@ -50,7 +50,7 @@ struct GemmEpilogue {
 };
 
 // C[b] = epilogue(A[b] (M x K) * B[b]^T (N x K)).  impl: 0 = tcgen05/TMA kernel, 1 = SIMT check kernel.
-int gemm_bf16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
+int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl);
 
 int device_sm_count();

@@ -1,0 +1,42 @@
+// Launchers of the non-GEMM kernels of the path (all stream-ordered, no syncs).
+#pragma once
+#include "model.cuh"
+
+namespace nb {
+
+// ---- frontend.cu: waveform -> conv0 + GroupNorm + GELU, LayerNorm(512)
+int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int B, int max_chunks, double* part);
+int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
+                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold);
+int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
+                       const float* fold, op_t* out);
+int launch_ln512(cudaStream_t st, const op_t* in, long long rows, const float* g, const float* b, op_t* out);
+
+// ---- encoder.cu
+int launch_pos_scatter(cudaStream_t st, const float* x, const UttMeta* meta, int B, long long frames,
+                       long long pos_rows_alloc, op_t* pos_g);
+// x = LN(x0 + y[pos row]) on valid frames, 0 elsewhere
+int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, const UttMeta* meta, int B,
+                         long long frames, const float* g, const float* b, float* x, op_t* xh);
+// x = LN(pre) on valid frames, 0 elsewhere; optional compact copy of the result (loss path):
+// layer_out[(utt * T + t) * 768 + c] for a uniform batch
+int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
+                 const float* b, float* x, op_t* xh, float* layer_out, int layer_T);
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out);
+int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
+                     const float* head_b, float* emb, float* pooled_out);
+
+// ---- distance.cu
+int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
+                      double* row_mean);
+
+__device__ __forceinline__ int find_utt_by_frame(const UttMeta* __restrict__ meta, int B, int f) {
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (meta[mid].frame0 <= f) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+}  // namespace nb

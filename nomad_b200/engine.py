@@ -1,0 +1,205 @@
+"""Thin host wrapper over the C ABI: owns the handle, torch-allocated workspaces and streams.
+
+PyTorch is used for device memory, streams and (in ``dist.py``) ``torch.distributed`` only; every
+arithmetic step of the path runs in ``libnomad_b200.so``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import EMB_DIM, NUM_LAYERS, SSL_OUT_DIM
+
+MIN_SAMPLES = 400
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One NOMAD model resident on one GPU."""
+
+    def __init__(self, state_dict, device: Optional[int] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.NomadB200Error("nomad_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if not torch.is_tensor(v) or k.endswith("mask_emb"):
+                continue
+            names.append(k.encode())
+            arrays.append(np.ascontiguousarray(v.detach().to(torch.float32).cpu().numpy()))
+        tens = (_lib.Tensor * len(names))()
+        for i, (n, a) in enumerate(zip(names, arrays)):
+            tens[i].name = n
+            tens[i].data = a.ctypes.data_as(C.c_void_p)
+            tens[i].numel = a.size
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_create(C.byref(h), tens, len(names), self.device_index), "nomad_b200_create")
+        self.handle = h
+        self._ws: Optional[torch.Tensor] = None
+        self._pinned: Optional[torch.Tensor] = None
+        self._pinned_out: Optional[torch.Tensor] = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.nomad_b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def set_gemm_impl(self, impl: int):
+        _lib.check(self.lib.nomad_b200_set_gemm_impl(self.handle, int(impl)), "set_gemm_impl")
+
+    def set_loss_head(self, weight: torch.Tensor, bias: torch.Tensor):
+        w = np.ascontiguousarray(weight.detach().to(torch.float32).cpu().numpy())
+        b = np.ascontiguousarray(bias.detach().to(torch.float32).cpu().numpy())
+        assert w.shape == (EMB_DIM, SSL_OUT_DIM) and b.shape == (EMB_DIM,)
+        _lib.check(self.lib.nomad_b200_set_loss_head(self.handle, w.ctypes.data_as(C.c_void_p),
+                                                     b.ctypes.data_as(C.c_void_p)), "set_loss_head")
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        """Grow-only device scratch (torch caching allocator), 1024-byte aligned."""
+        if self._ws is None or self._ws.numel() < nbytes + 1024:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 2048, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _aligned(ws: torch.Tensor):
+        base = ws.data_ptr()
+        off = (-base) % 1024
+        return C.c_void_p(base + off), ws.numel() - off
+
+    @staticmethod
+    def offsets(lengths: Sequence[int]):
+        off = np.zeros(len(lengths) + 1, dtype=np.int64)
+        np.cumsum(np.asarray(lengths, dtype=np.int64), out=off[1:])
+        return off
+
+    # ------------------------------------------------------------------ scoring
+    def embed_packed(self, wav: torch.Tensor, offsets: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``wav``: 1-D fp32 CUDA tensor holding the utterances back to back; ``offsets``: B+1 int64 (host)."""
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous()
+        B = len(offsets) - 1
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        need = self.lib.nomad_b200_embed_workspace_bytes(off_p, B)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        ws = self.workspace(need)
+        wp, wbytes = self._aligned(ws)
+        if out is None:
+            out = torch.empty((B, EMB_DIM), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_embed(self.handle, _ptr(wav), off_p, B, _ptr(out), wp, wbytes, _stream_ptr()),
+                       "nomad_b200_embed")
+        return out
+
+    def embed(self, waves: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Variable-length batch: list of 1-D (or (1, N)) fp32 tensors on any device -> (B, 256) CUDA tensor."""
+        flat = [w.reshape(-1).to(torch.float32) for w in waves]
+        offsets = self.offsets([int(w.numel()) for w in flat])
+        wav = torch.cat([w.to(self.device, non_blocking=True) for w in flat])
+        return self.embed_packed(wav, offsets)
+
+    def embed_host(self, wav_host: np.ndarray, offsets: np.ndarray, emb_host: Optional[np.ndarray] = None) -> np.ndarray:
+        """HOST buffers in and out through ``nomad_b200_embed_host`` (H2D + compute + D2H + sync inside)."""
+        B = len(offsets) - 1
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        need = self.lib.nomad_b200_embed_workspace_bytes(off_p, B)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        total = int(offsets[-1] - offsets[0])
+        ws = self.workspace(need + 4 * total + 1024 * B + 8192)
+        wp, wbytes = self._aligned(ws)
+        if emb_host is None:
+            emb_host = np.empty((B, EMB_DIM), dtype=np.float32)
+        assert wav_host.dtype == np.float32 and wav_host.flags.c_contiguous
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_embed_host(self.handle, wav_host.ctypes.data_as(C.c_void_p), off_p, B,
+                                                      emb_host.ctypes.data_as(C.c_void_p), wp, wbytes, _stream_ptr()),
+                       "nomad_b200_embed_host")
+        return emb_host
+
+    # ------------------------------------------------------------------ loss-side forward
+    def num_frames(self, n: int) -> int:
+        return int(self.lib.nomad_b200_num_frames(int(n)))
+
+    def layers(self, wav: torch.Tensor, want_layers: bool = True, want_emb: bool = True):
+        """``LossNetLayers.forward`` for a (B, N) or (B, 1, N) CUDA batch -> ((12, B, T, 768) | None, (B, 256) | None)."""
+        if wav.dim() == 3:
+            wav = wav.squeeze(1)
+        wav = wav.to(self.device, torch.float32).contiguous()
+        B, N = wav.shape
+        T = self.num_frames(N)
+        need = self.lib.nomad_b200_layers_workspace_bytes(B, N)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        ws = self.workspace(need)
+        wp, wbytes = self._aligned(ws)
+        layers = torch.empty((NUM_LAYERS, B, T, SSL_OUT_DIM), dtype=torch.float32, device=self.device) if want_layers else None
+        emb = torch.empty((B, EMB_DIM), dtype=torch.float32, device=self.device) if want_emb else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_layers_fwd(self.handle, _ptr(wav), B, N, _ptr(layers), _ptr(emb), wp, wbytes,
+                                                      _stream_ptr()), "nomad_b200_layers_fwd")
+        return layers, emb
+
+    def loss_fwd_bwd(self, est: torch.Tensor, clean: torch.Tensor, feature_grad_mult: float, with_grad: bool = True):
+        if est.dim() == 3:
+            est = est.squeeze(1)
+        if clean.dim() == 3:
+            clean = clean.squeeze(1)
+        est = est.detach().to(self.device, torch.float32).contiguous()
+        clean = clean.detach().to(self.device, torch.float32).contiguous()
+        assert est.shape == clean.shape
+        B, N = est.shape
+        need = self.lib.nomad_b200_loss_workspace_bytes(B, N, 1 if with_grad else 0)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        ws = self.workspace(need)
+        wp, wbytes = self._aligned(ws)
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        grad = torch.empty_like(est) if with_grad else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_loss_fwd_bwd(self.handle, _ptr(est), _ptr(clean), B, N,
+                                                        C.c_float(feature_grad_mult), _ptr(loss), _ptr(grad), wp, wbytes,
+                                                        _stream_ptr()), "nomad_b200_loss_fwd_bwd")
+        return loss, grad
+
+    # ------------------------------------------------------------------ distance
+    def cdist_mean(self, deg: torch.Tensor, nmr: torch.Tensor, want_matrix: bool = True, gemm_impl: int = 0):
+        """(n, 256), (m, 256) fp32 CUDA -> ((n, m) fp32 | None, (n,) fp64 row means)."""
+        deg = deg.to(self.device, torch.float32).contiguous()
+        nmr = nmr.to(self.device, torch.float32).contiguous()
+        n, m = deg.shape[0], nmr.shape[0]
+        dm = torch.empty((n, m), dtype=torch.float32, device=self.device) if want_matrix else None
+        mean = torch.empty((n,), dtype=torch.float64, device=self.device)
+        need = self.lib.nomad_b200_cdist_workspace_bytes(n, m)
+        ws = self.workspace(need)
+        wp, wbytes = self._aligned(ws)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_cdist_mean(_ptr(deg), n, _ptr(nmr), m, _ptr(dm), _ptr(mean), wp, wbytes,
+                                                      gemm_impl, _stream_ptr()), "nomad_b200_cdist_mean")
+        return dm, mean
+
+    def launch_count(self) -> int:
+        return int(self.lib.nomad_b200_launch_count())

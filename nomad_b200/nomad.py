@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's ``nomad_audio.nomad`` module (``src/nomad_audio/nomad.py``).
+
+Same class and method names, argument meaning, return values, CSV formats and error messages as the
+reference; the arithmetic (wav2vec 2.0 base forward, pooled head, pairwise distance, loss and its
+backward) runs in ``libnomad_b200.so`` on a B200.  Differences that are deliberate:
+
+* files are embedded in length-bucketed batches instead of one by one (``nomad.py:166-189``); every
+  utterance is still computed exactly as if alone (length-masked), so results equal the per-file loop;
+* there is no CPU path: ``device='cpu'`` raises;
+* weights come from ``pt-models/nomad_best_model.pt`` (or ``$NOMAD_B200_CHECKPOINT``) when present,
+  else seeded random-init of the identical architecture -- nothing is downloaded at import;
+* ``forward`` back-propagates to ``estimate`` only (dgrad chain, wheel 0.0.8 semantics: the NOMAD
+  network's own parameters receive no ``.grad``).
+"""
+from __future__ import annotations
+
+import os
+from datetime import datetime
+from typing import List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import audio
+from .engine import Engine, MIN_SAMPLES
+from .weights import EMB_DIM, SSL_OUT_DIM, load_state_dict
+
+w2v_path = 'pt-models/wav2vec_small.pt'        # kept for API compatibility (nomad.py:21); unused
+nomad_path = 'pt-models/nomad_best_model.pt'   # nomad.py:29
+
+
+def plan_batches(lengths: Sequence[int], max_samples: int) -> List[List[int]]:
+    """Length-bucketed batches: indices sorted by length, cut when the sample budget is reached.
+    Returns index lists; results are scattered back so output order == input order."""
+    order = sorted(range(len(lengths)), key=lambda i: (lengths[i], i))
+    batches, cur, tot = [], [], 0
+    for i in order:
+        n = int(lengths[i])
+        if cur and tot + n > max_samples:
+            batches.append(cur)
+            cur, tot = [], 0
+        cur.append(i)
+        tot += n
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+class TripletModel:
+    """``TripletModel`` (``nomad.py:214-231``): ``model(wav, lengths=None) -> (B, 256)`` unit-norm."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.ssl_features = SSL_OUT_DIM
+
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    def __call__(self, wav, lengths=None):  # ``lengths`` accepted and ignored, as in the reference
+        return self.forward(wav, lengths)
+
+    @torch.no_grad()
+    def forward(self, wav: torch.Tensor, lengths=None) -> torch.Tensor:
+        if wav.dim() == 3:
+            wav = wav.squeeze(1)  # nomad.py:225
+        if wav.dim() == 1:
+            wav = wav.unsqueeze(0)
+        B, N = wav.shape
+        flat = wav.to(self.engine.device, torch.float32).contiguous().reshape(-1)
+        return self.engine.embed_packed(flat, np.arange(B + 1, dtype=np.int64) * N)
+
+
+class LossNetLayers:
+    """``LossNetLayers`` (``nomad.py:233-258``): 12 transformer-layer outputs + the head output."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.ssl_features = SSL_OUT_DIM
+        # freshly initialised head, exactly like the reference (nomad.py:238-241)
+        self.embedding_layer = nn.Sequential(nn.ReLU(), nn.Linear(SSL_OUT_DIM, EMB_DIM))
+        self._synced = None
+
+    def to(self, *_a, **_k):
+        return self
+
+    def sync_head(self):
+        lin = self.embedding_layer[1]
+        key = (lin.weight._version, lin.bias._version, lin.weight.data_ptr(), lin.bias.data_ptr())
+        if key != self._synced:
+            self.engine.set_loss_head(lin.weight, lin.bias)
+            self._synced = key
+
+    def __call__(self, wav):
+        return self.forward(wav)
+
+    @torch.no_grad()
+    def forward(self, wav: torch.Tensor) -> List[torch.Tensor]:
+        self.sync_head()
+        layers, emb = self.engine.layers(wav)
+        return [layers[i] for i in range(layers.shape[0])] + [emb]
+
+
+class NomadLoss(nn.Module):
+    """``NomadLoss`` (``nomad.py:260-282``) on already-computed feature lists."""
+
+    def __init__(self):
+        super().__init__()
+        self.L = 13
+        self.only_embedding = False
+
+    def forward(self, nomad_ref, nomad_test):
+        l1_dist = 0.0
+        for i in range(self.L):
+            l1_dist = l1_dist + F.l1_loss(nomad_test[i], nomad_ref[i])
+        return l1_dist
+
+
+class _NomadLossFn(torch.autograd.Function):
+    """loss = sum_i mean|H_i(est) - H_i(clean)|; d loss / d est comes back from the same C call."""
+
+    @staticmethod
+    def forward(ctx, estimate, clean, owner):
+        need_grad = estimate.requires_grad
+        loss, grad = owner.engine.loss_fwd_bwd(estimate, clean, owner.feature_grad_mult, with_grad=need_grad)
+        ctx.shape = estimate.shape
+        ctx.out_device = estimate.device
+        ctx.out_dtype = estimate.dtype
+        ctx.save_for_backward(grad if grad is not None else torch.empty(0))
+        out = loss.to(estimate.device)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        if g.numel() == 0:
+            return None, None, None
+        ge = (g * grad_out.to(g.device)).reshape(ctx.shape).to(ctx.out_device, ctx.out_dtype)
+        return ge, None, None
+
+
+class Nomad():
+    def __init__(self, device=None, checkpoint: Optional[str] = None, seed: int = 1234,
+                 feature_grad_mult: float = 0.1, max_batch_seconds: float = 2000.0, state_dict=None):
+        # *** DEVICE SETTINGS *** (nomad.py:38-49)
+        if torch.cuda.is_available():
+            self.DEVICE = 'cuda'
+        else:
+            self.DEVICE = 'cpu'
+        if device is not None:
+            self.DEVICE = device
+        if not str(self.DEVICE).startswith('cuda'):
+            raise RuntimeError(f"nomad_b200 runs on CUDA (B200, sm_100a) only; device={self.DEVICE!r} has no "
+                               "implementation here (there is no CPU fallback)")
+        print(f'NOMAD running on: {self.DEVICE}')
+        dev = torch.device(self.DEVICE)
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+
+        # *** LOAD MODEL *** (nomad.py:51-68): tensors only, no fairseq needed
+        if state_dict is None:
+            state_dict, self.weights_source = load_state_dict(checkpoint, seed)
+        else:
+            self.weights_source = "state_dict"
+        self.engine = Engine(state_dict, index)
+        self.model = TripletModel(self.engine)
+        # NOMAD loss model shares the same network (nomad.py:70-72)
+        self.lossnet_layers = LossNetLayers(self.engine)
+        self.nomad_loss = NomadLoss()
+        # fairseq applies GradMultiply(feature_grad_mult) to the conv features (wav2vec 2.0 base: 0.1)
+        self.feature_grad_mult = float(feature_grad_mult)
+        self.max_batch_samples = int(max_batch_seconds * 16000)
+
+    def predict(self, mode='dir', nmr='data/nmr-data', deg='data/test-data', results_path=None):
+        if nmr is None:
+            raise Exception('nmr_path not specified, you need to pass a valid value to nmr_path')
+        if deg is None:
+            raise Exception('test_path not specified, you need to pass a valide value to test_path')
+
+        if mode == 'dir':
+            if os.path.isdir(nmr) == False:
+                raise Exception(f'Path to the non-matching reference files {nmr} does not exist')
+            if os.path.isdir(deg) == False:
+                raise Exception(f'Path to the test files {deg} does not exist')
+        elif mode == 'csv':
+            if os.path.isfile(nmr) == False:
+                raise Exception(f'File {nmr} does not exist')
+            if os.path.isfile(deg) == False:
+                raise Exception(f'File {deg} does not exist')
+        else:
+            raise Exception(f'Mode value {mode} is not valid. Valid values are dir and csv')
+
+        print(f'Compute non-matching reference embeddings from {nmr}')
+        nmr_embeddings = self.get_embeddings(nmr).set_index('filename')
+
+        print(f'Compute degraded embeddings from {deg}')
+        test_embeddings = self.get_embeddings(deg).set_index('filename')
+
+        # Pairwise distance matrix + row mean (nomad.py:108,111) on the GPU
+        distance_matrix, avg_nomad = self.pairwise(test_embeddings, nmr_embeddings)
+
+        test_files = [x.split('/')[-1].split('.')[0] for x in test_embeddings.index]
+        df_avg_nomad = pd.DataFrame({'Test File': test_files, 'NOMAD': avg_nomad}).set_index('Test File').round(3)
+
+        df_dm = pd.DataFrame(distance_matrix).round(3)
+        df_dm['Test File'] = test_files
+        df_dm.set_index('Test File', inplace=True)
+        df_dm.columns = [x.split('/')[-1].split('.')[0] for x in nmr_embeddings.index]
+
+        # Save results (nomad.py:122-139)
+        if results_path == None:
+            now = datetime.now()
+            dt_string = now.strftime("%d-%m-%Y_%H-%M-%S")
+            results_avg_path = os.path.join('results-csv', dt_string)
+            if os.path.isdir(results_avg_path) == False:
+                os.makedirs(results_avg_path)
+            results_scores_path = os.path.join('results-csv', dt_string)
+            if os.path.isdir(results_scores_path) == False:
+                os.makedirs(results_scores_path)
+            results_avg_path = os.path.join(results_avg_path, f'{dt_string}_nomad_avg.csv')
+            results_scores_path = os.path.join(results_scores_path, f'{dt_string}_nomad_scores.csv')
+        else:
+            results_avg_path = os.path.join(results_path, 'nomad_avg.csv')
+            results_scores_path = os.path.join(results_path, 'nomad_scores.csv')
+
+        df_avg_nomad.reset_index().to_csv(results_avg_path, index=False)
+        df_dm.reset_index().to_csv(results_scores_path, index=False)
+        return df_avg_nomad, df_dm
+
+    def pairwise(self, test_embeddings, nmr_embeddings):
+        """``cdist`` + ``np.mean(axis=1)`` -> (float64 (N, M), float64 (N,)) like scipy/numpy return."""
+        te = np.ascontiguousarray(np.asarray(test_embeddings, dtype=np.float32))
+        ne = np.ascontiguousarray(np.asarray(nmr_embeddings, dtype=np.float32))
+        if te.ndim != 2 or ne.ndim != 2 or te.shape[1] != ne.shape[1]:
+            raise ValueError('XA and XB must have the same number of columns (i.e. feature dimension.)')
+        dm, mean = self.engine.cdist_mean(torch.from_numpy(te), torch.from_numpy(ne))
+        return dm.cpu().numpy().astype(np.float64), mean.cpu().numpy()
+
+    def forward(self, estimate, clean):
+        """Differentiable NOMAD loss (``nomad.py:142-146``): 0-dim tensor, grad flows to ``estimate``."""
+        self.lossnet_layers.sync_head()
+        return _NomadLossFn.apply(estimate, clean, self)
+
+    def get_embeddings(self, path):
+        # If mode == dir
+        if os.path.isdir(path):
+            data = pd.DataFrame(os.listdir(path))
+            data.columns = ['filename']
+            data['filename'] = [os.path.join(path, x) for x in data['filename']]
+        # If mode == csv
+        elif os.path.isfile(path):
+            data = pd.read_csv(path)
+            if 'filename' not in data.columns:
+                raise Exception('File {path} not including a column called filename. Please pass a csv file with a column called filename that includes the absolute filpaths of the waveforms.')
+
+        embeddings = self.get_embeddings_csv(self.model, data)
+        return embeddings
+
+    def embed_waves(self, waves: Sequence[torch.Tensor]) -> np.ndarray:
+        """Embed variable-length mono waveforms in length-bucketed batches; output order == input order."""
+        lengths = [int(w.numel()) for w in waves]
+        out = np.empty((len(waves), EMB_DIM), dtype=np.float32)
+        for idx in plan_batches(lengths, self.max_batch_samples):
+            emb = self.engine.embed([waves[i] for i in idx])
+            out[idx] = emb.cpu().numpy()
+        return out
+
+    # Function that extract NOMAD embeddings and store them in a DataFrame (nomad.py:166-189)
+    def get_embeddings_csv(self, model, file_names, root=False):
+        file_names_arr = np.array(file_names)
+        waves = []
+        for filename_anchor in file_names_arr:
+            if root:
+                filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
+            else:
+                filepath = filename_anchor
+            wave = self.load_processing(filepath, trim=False)
+            if wave.shape[-1] < MIN_SAMPLES:
+                raise RuntimeError(f"Calculated padded input size per channel: ({wave.shape[-1]}). Kernel size: (10). "
+                                   "Kernel size can't be greater than actual input size")
+            waves.append(wave.reshape(-1))
+        embeddings = self.embed_waves(waves) if waves else np.zeros((0, EMB_DIM), dtype=np.float32)
+        embeddings = pd.DataFrame(embeddings)
+        df_emb = pd.concat([file_names.reset_index(), embeddings], axis=1).drop('index', axis=1)
+        return df_emb
+
+    # Load wave file (nomad.py:192-212)
+    def load_processing(self, filepath, target_sr=16000, trim=False):
+        return audio.load_processing(filepath, target_sr, trim)

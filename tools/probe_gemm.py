@@ -37,41 +37,41 @@ def run_case(name):
     M, N, K, lda, wrap, batch, flags = CASES[name]
     impl = 1 if name.startswith("simt") else 0
     lib = C.CDLL(_lib.LIB_PATH)
-    for fn in ("nomad_b200_gemm_bf16", "nomad_b200_last_error"):
+    for fn in ("nomad_b200_gemm_f16", "nomad_b200_last_error"):
         getattr(lib, fn).restype, getattr(lib, fn).argtypes = _lib.PROTOTYPES[fn]
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(1)
     lda_ = lda or K
     if lda and batch == 1:
         rows = M + (K + lda - 1) // lda + 1
-        a_buf = (torch.randn(rows * lda, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        a_buf = (torch.randn(rows * lda, generator=g) * 0.5).to(torch.float16).to(dev)
         a_rows = rows if wrap else M
         a_bs = 0
         idx = (torch.arange(M, device=dev)[:, None] * lda + torch.arange(K, device=dev)[None, :])
         a_mat = a_buf[idx].float()[None]
     elif lda:  # grouped, overlapping rows (pos-conv like): per batch buffer of (M + K/lda) rows of lda
         rows = M + K // lda
-        a_buf = (torch.randn(batch, rows * lda, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        a_buf = (torch.randn(batch, rows * lda, generator=g) * 0.5).to(torch.float16).to(dev)
         a_rows = M
         a_bs = rows * lda
         idx = (torch.arange(M, device=dev)[:, None] * lda + torch.arange(K, device=dev)[None, :])
         a_mat = a_buf[:, idx].float()
     else:
-        a_buf = (torch.randn(batch, M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        a_buf = (torch.randn(batch, M, K, generator=g) * 0.5).to(torch.float16).to(dev)
         a_rows = M
         a_bs = M * K
         a_mat = a_buf.float()
-    b = (torch.randn(batch, N, K, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    b = (torch.randn(batch, N, K, generator=g) * 0.05).to(torch.float16).to(dev)
     bias = torch.randn(batch, N, generator=g).to(dev)
     ldc = N * batch if batch > 1 else N
     c_bs = N if batch > 1 else 0
     resid = torch.randn(M, ldc, generator=g).to(dev)
     cf = torch.full((M, ldc), float("nan"), device=dev)
-    ch = torch.full((M, ldc), float("nan"), device=dev, dtype=torch.bfloat16)
+    ch = torch.full((M, ldc), float("nan"), device=dev, dtype=torch.float16)
     st = torch.cuda.current_stream().cuda_stream
 
     def call():
-        r = lib.nomad_b200_gemm_bf16(a_buf.data_ptr(), a_rows, lda_, wrap, b.data_ptr(), M, N, K, batch, a_bs, N * K,
+        r = lib.nomad_b200_gemm_f16(a_buf.data_ptr(), a_rows, lda_, wrap, b.data_ptr(), M, N, K, batch, a_bs, N * K,
                                      c_bs, bias.data_ptr(), resid.data_ptr(), cf.data_ptr(), ch.data_ptr(), ldc,
                                      flags, impl, st)
         if r != 0:
@@ -92,7 +92,7 @@ def run_case(name):
     if flags & 8:
         out["f32"] = (cf - ref).abs().max().item()
     if flags & 16:
-        out["bf16"] = (ch.float() - ref).abs().max().item()
+        out["op_t"] = (ch.float() - ref).abs().max().item()
     scale = ref.abs().max().item()
     msg = f"[{name}] M={M} N={N} K={K} lda={lda_} wrap={wrap} batch={batch} flags={flags} impl={impl} max|ref|={scale:.3f} err={out}"
     if M * N * K * batch > 1e10:
