@@ -116,6 +116,12 @@ NOMAD_B200_API int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_
                          const float* bias, const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags,
                          int gemm_impl, void* stream);
 
+/* In-situ timing of the tensor-core GEMM launches (one CUDA event pair per launch, on the launching
+ * stream) for the roofline leg of bench.py: enable, run steps, read the summed device time (ms), the
+ * algorithmic FLOPs (2*M*N*K) and the launch count; reading synchronises on the recorded events. */
+NOMAD_B200_API int nomad_b200_profile_gemm(int enable);
+NOMAD_B200_API int nomad_b200_profile_gemm_read(double* total_ms, double* total_flops, int64_t* launches);
+
 /* Number of kernels this library has launched in this process (bench.py's ``gpu_launches``). */
 NOMAD_B200_API int64_t nomad_b200_launch_count(void);
 

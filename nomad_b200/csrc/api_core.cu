@@ -28,6 +28,17 @@ const char* nomad_b200_last_error(void) { return nb::get_error(); }
 const char* nomad_b200_version(void) { return "nomad_b200 0.1 (sm_100a)"; }
 int64_t nomad_b200_launch_count(void) { return nb::g_launches.load(); }
 
+int nomad_b200_profile_gemm(int enable) {
+    nb::gemm_profile_enable(enable != 0);
+    return 0;
+}
+int nomad_b200_profile_gemm_read(double* total_ms, double* total_flops, int64_t* launches) {
+    long long n = 0;
+    int r = nb::gemm_profile_read(total_ms, total_flops, &n);
+    *launches = n;
+    return r;
+}
+
 int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_t lda, int k_wrap, const void* b_f16, int m, int n,
                          int k, int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride, const float* bias,
                          const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags, int gemm_impl,

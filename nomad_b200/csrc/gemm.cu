@@ -7,6 +7,7 @@
 #include "gemm.cuh"
 
 #include <mutex>
+#include <vector>
 
 namespace nb {
 
@@ -346,6 +347,57 @@ int device_sm_count() {
     return sms[dev];
 }
 
+// In-situ timing of the tensor-core GEMM launches (bench.py's roofline leg): one CUDA event pair per
+// launch on the launching stream, read back after the timed region.
+struct GemmProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<double> flops;
+    size_t used = 0;
+};
+static GemmProfile g_prof;
+
+void gemm_profile_enable(bool on) {
+    g_prof.on = on;
+    g_prof.used = 0;
+    g_prof.flops.clear();
+}
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+    double ms = 0.0, fl = 0.0;
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        NB_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+        float t = 0.f;
+        NB_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+        ms += t;
+        fl += g_prof.flops[i];
+    }
+    *total_ms = ms;
+    *total_flops = fl;
+    *launches = (long long)g_prof.used;
+    g_prof.used = 0;
+    g_prof.flops.clear();
+    return 0;
+}
+static int prof_begin(cudaStream_t st, double flops) {
+    if (!g_prof.on) return 0;
+    if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
+        cudaEvent_t a, b;
+        NB_CUDA(cudaEventCreate(&a));
+        NB_CUDA(cudaEventCreate(&b));
+        g_prof.ev.push_back(a);
+        g_prof.ev.push_back(b);
+    }
+    g_prof.flops.push_back(flops);
+    NB_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used], st));
+    return 0;
+}
+static int prof_end(cudaStream_t st) {
+    if (!g_prof.on) return 0;
+    NB_CUDA(cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st));
+    g_prof.used++;
+    return 0;
+}
+
 template <int BN>
 static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = TileCfg<BN>;
@@ -362,8 +414,10 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     const long long tiles = (long long)args.m_tiles * args.n_tiles * args.batch;
     int grid = device_sm_count();
     if (tiles < grid) grid = (int)tiles;
+    NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
     gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
     NB_LAUNCHED();
+    NB_TRY(prof_end(st));
     return 0;
 }
 

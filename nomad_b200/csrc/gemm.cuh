@@ -55,4 +55,8 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
 
 int device_sm_count();
 
+// event-pair timing of every tensor-core GEMM launch while enabled (see bench.py)
+void gemm_profile_enable(bool on);
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
+
 }  // namespace nb

@@ -203,13 +203,18 @@ class Nomad():
         # Pairwise distance matrix + row mean (nomad.py:108,111) on the GPU
         distance_matrix, avg_nomad = self.pairwise(test_embeddings, nmr_embeddings)
 
-        test_files = [x.split('/')[-1].split('.')[0] for x in test_embeddings.index]
+        return self.write_results(list(test_embeddings.index), list(nmr_embeddings.index), distance_matrix, avg_nomad,
+                                  results_path)
+
+    def write_results(self, test_index, nmr_index, distance_matrix, avg_nomad, results_path=None):
+        """DataFrame assembly + the two CSVs, byte-compatible with the reference (``nomad.py:113-140``)."""
+        test_files = [x.split('/')[-1].split('.')[0] for x in test_index]
         df_avg_nomad = pd.DataFrame({'Test File': test_files, 'NOMAD': avg_nomad}).set_index('Test File').round(3)
 
         df_dm = pd.DataFrame(distance_matrix).round(3)
         df_dm['Test File'] = test_files
         df_dm.set_index('Test File', inplace=True)
-        df_dm.columns = [x.split('/')[-1].split('.')[0] for x in nmr_embeddings.index]
+        df_dm.columns = [x.split('/')[-1].split('.')[0] for x in nmr_index]
 
         # Save results (nomad.py:122-139)
         if results_path == None:

@@ -160,3 +160,13 @@ def conv_out_lengths(n_samples: int) -> list:
         t = (t - k) // s + 1 if t >= k else 0
         out.append(t)
     return out
+
+
+def flops_embed(n_samples: int) -> float:
+    """Algorithmic forward FLOPs F(N) of one utterance: conv stack, projection,
+    positional conv, 12 x (qkv + out-proj, FFN, attention core), head."""
+    T = conv_out_lengths(n_samples)
+    T6 = T[6]
+    return (2.0 * (5120 * T[0] + 786432 * (T[1] + T[2] + T[3] + T[4]) + 524288 * (T[5] + T[6]))
+            + 786432.0 * T6 + 9437184.0 * T6
+            + 12.0 * (4718592.0 * T6 + 9437184.0 * T6 + 3072.0 * T6 * T6) + 393216.0)

@@ -1,0 +1,274 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden outputs of the reference.  Tolerances: embeddings / scores max-abs <= 1e-3 (fp16 tensor-core
+operands, fp32 accumulate -- the north star's bf16/tf32 class); cdist on given embeddings <= 1e-5;
+ordering bit-exact."""
+import ctypes as C
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+EMB_TOL = 1e-3
+LAYER_TOL = 2.5e-2  # per-element, layer outputs have |x| up to ~4 (fp16 operand rounding accumulates over 12 layers)
+
+
+@pytest.fixture(scope="module")
+def engine(state_dict):
+    from nomad_b200.engine import Engine
+    return Engine(state_dict, 0)
+
+
+def _load_wav(path):
+    with wave.open(path, "rb") as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    return torch.from_numpy(pcm.astype(np.float32) / 32768.0)
+
+
+def _split(flat, lens):
+    out, o = [], 0
+    for n in lens:
+        out.append(flat[o:o + n]); o += n
+    return out
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,lda,wrap,batch,flags", [
+    (128, 256, 64, 0, 0, 1, 8), (1000, 768, 512, 0, 0, 1, 1 | 2 | 16), (777, 3072, 768, 0, 0, 1, 1 | 2 | 16),
+    (515, 768, 3072, 0, 0, 1, 1 | 4 | 8 | 16), (700, 128, 256, 0, 0, 1, 8), (700, 64, 256, 0, 0, 1, 8),
+    (999, 512, 1536, 1024, 0, 1, 2 | 16), (999, 512, 1536, 1024, 1024, 1, 2 | 16), (300, 48, 6144, 48, 0, 16, 16),
+    (1, 768, 512, 0, 0, 1, 8), (129, 2304, 768, 0, 0, 1, 1 | 16),
+])
+def test_gemm_tcgen05_vs_torch_and_simt(M, N, K, lda, wrap, batch, flags):
+    from nomad_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + K)
+    lda_ = lda or K
+    if lda and batch == 1:
+        rows = M + (K + lda - 1) // lda + 1
+        a_buf = (torch.randn(rows * lda, generator=g) * 0.5).half().to(dev)
+        a_rows, a_bs = (rows if wrap else M), 0
+        idx = torch.arange(M, device=dev)[:, None] * lda + torch.arange(K, device=dev)[None, :]
+        a_mat = a_buf[idx].float()[None]
+    elif lda:
+        rows = M + K // lda
+        a_buf = (torch.randn(batch, rows * lda, generator=g) * 0.5).half().to(dev)
+        a_rows, a_bs = M, rows * lda
+        idx = torch.arange(M, device=dev)[:, None] * lda + torch.arange(K, device=dev)[None, :]
+        a_mat = a_buf[:, idx].float()
+    else:
+        a_buf = (torch.randn(batch, M, K, generator=g) * 0.5).half().to(dev)
+        a_rows, a_bs = M, M * K
+        a_mat = a_buf.float()
+    b = (torch.randn(batch, N, K, generator=g) * 0.05).half().to(dev)
+    bias = torch.randn(batch, N, generator=g).to(dev)
+    ldc = N * batch
+    c_bs = N if batch > 1 else 0
+    resid = torch.randn(M, ldc, generator=g).to(dev)
+    outs = {}
+    for impl in (0, 1):
+        cf = torch.full((M, ldc), float("nan"), device=dev)
+        ch = torch.full((M, ldc), float("nan"), device=dev, dtype=torch.float16)
+        _lib.check(lib.nomad_b200_gemm_f16(a_buf.data_ptr(), a_rows, lda_, wrap, b.data_ptr(), M, N, K, batch, a_bs,
+                                           N * K, c_bs, bias.data_ptr(), resid.data_ptr(), cf.data_ptr(), ch.data_ptr(),
+                                           ldc, flags, impl, torch.cuda.current_stream().cuda_stream), "gemm")
+        torch.cuda.synchronize()
+        outs[impl] = (cf, ch)
+    ref = torch.einsum("bmk,bnk->bmn", a_mat.double(), b.double())
+    if flags & 1:
+        ref = ref + bias[:, None, :].double()
+    if flags & 2:
+        ref = torch.nn.functional.gelu(ref)
+    ref = ref.permute(1, 0, 2).reshape(M, batch * N)
+    if flags & 4:
+        ref = ref + resid.double()
+    scale = max(1.0, ref.abs().max().item())
+    for impl in (0, 1):
+        cf, ch = outs[impl]
+        if flags & 8:
+            assert (cf.double() - ref).abs().max().item() <= 2e-5 * scale
+        if flags & 16:
+            assert (ch.double() - ref).abs().max().item() <= 1.5e-3 * scale
+    if flags & 8:  # tensor-core and SIMT kernels agree to fp32 accumulation-order noise
+        assert (outs[0][0] - outs[1][0]).abs().max().item() <= 2e-5 * scale
+
+
+# ------------------------------------------------------------------------------- golden fixtures
+def test_layers_and_embeddings_small_batch(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_small.npz"))
+    wav = torch.from_numpy(g["wav_b"]).cuda()
+    layers, _ = engine.layers(wav)
+    layers = layers.cpu().numpy()
+    assert layers.shape == g["layers_b"].shape
+    for l in range(12):
+        assert np.abs(layers[l] - g["layers_b"][l]).max() <= LAYER_TOL, l
+    emb = engine.embed([wav[i] for i in range(wav.shape[0])]).cpu().numpy()
+    assert np.abs(emb - g["emb_b"]).max() <= EMB_TOL
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+def test_variable_length_batch_equals_per_file_reference(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_small.npz"))
+    waves = _split(torch.from_numpy(g["wav_v"]), g["lens"].tolist())
+    emb = engine.embed(waves).cpu().numpy()
+    assert np.abs(emb - g["emb_v"]).max() <= EMB_TOL
+    # batch composition must not matter: each utterance alone gives the same bits
+    for i in (0, 3, 7):
+        alone = engine.embed([waves[i]]).cpu().numpy()[0]
+        np.testing.assert_array_equal(alone, emb[i])
+    # order of utterances in the batch must not matter either
+    perm = [5, 2, 7, 0, 3, 6, 1, 4]
+    emb_p = engine.embed([waves[i] for i in perm]).cpu().numpy()
+    np.testing.assert_array_equal(emb_p, emb[perm])
+
+
+def test_too_short_input_is_rejected(engine):
+    from nomad_b200._lib import NomadB200Error
+    with pytest.raises(NomadB200Error, match="at least 400"):
+        engine.embed([torch.zeros(399)])
+    assert engine.embed([torch.zeros(400)]).shape == (1, 256)
+
+
+def test_bundled_wavs_against_reference_predict(engine, golden_dir, tmp_path, state_dict):
+    from nomad_b200.nomad import Nomad
+    g = np.load(os.path.join(golden_dir, "ref_predict.npz"))
+    nmr_dir = os.path.join(golden_dir, "wavs", "nmr-data")
+    deg_dir = os.path.join(golden_dir, "wavs", "test-data")
+    nomad = Nomad(state_dict=state_dict)
+    df_avg, df_dm = nomad.predict("dir", nmr_dir, deg_dir, str(tmp_path))
+    # ordering: bit-exact with the reference's rule (os.listdir order, stems)
+    stem = lambda f: f.split("/")[-1].split(".")[0]
+    assert list(df_avg.index) == [stem(f) for f in os.listdir(deg_dir)]
+    assert list(df_dm.index) == [stem(f) for f in os.listdir(deg_dir)]
+    assert list(df_dm.columns) == [stem(f) for f in os.listdir(nmr_dir)]
+    assert df_avg.index.name == "Test File" and list(df_avg.columns) == ["NOMAD"]
+    # values: compare by label against the reference's unrounded matrix
+    ref_dm = {(stem(d), stem(n)): g["dm"][i, j] for i, d in enumerate(g["deg_files"]) for j, n in enumerate(g["nmr_files"])}
+    ref_avg = {stem(d): g["avg"][i] for i, d in enumerate(g["deg_files"])}
+    emb_n = nomad.get_embeddings(nmr_dir).set_index("filename")
+    emb_d = nomad.get_embeddings(deg_dir).set_index("filename")
+    ref_emb = {f: g["nmr_emb"][i] for i, f in enumerate(g["nmr_files"])}
+    ref_emb.update({f: g["deg_emb"][i] for i, f in enumerate(g["deg_files"])})
+    for df in (emb_n, emb_d):
+        for path, row in df.iterrows():
+            assert np.abs(row.to_numpy(dtype=np.float32) - ref_emb[os.path.basename(path)]).max() <= EMB_TOL
+    dm, avg = nomad.pairwise(emb_d, emb_n)
+    assert dm.dtype == np.float64 and avg.dtype == np.float64
+    for i, d in enumerate(emb_d.index):
+        assert abs(avg[i] - ref_avg[stem(d)]) <= EMB_TOL
+        assert abs(df_avg.loc[stem(d), "NOMAD"] - round(ref_avg[stem(d)], 3)) <= 1.001e-3
+        for j, n in enumerate(emb_n.index):
+            assert abs(dm[i, j] - ref_dm[(stem(d), stem(n))]) <= EMB_TOL
+            assert abs(df_dm.loc[stem(d), stem(n)] - round(ref_dm[(stem(d), stem(n))], 3)) <= 1.001e-3
+    # the CSVs exist, have the reference's headers, and parse back to the frames
+    import pandas as pd
+    a = pd.read_csv(tmp_path / "nomad_avg.csv")
+    s = pd.read_csv(tmp_path / "nomad_scores.csv")
+    assert list(a.columns) == ["Test File", "NOMAD"]
+    assert list(s.columns) == ["Test File"] + list(df_dm.columns)
+    np.testing.assert_allclose(a["NOMAD"].to_numpy(), df_avg["NOMAD"].to_numpy())
+    # csv mode (single 'filename' column of paths) gives the same scores
+    csv_n, csv_d = tmp_path / "n.csv", tmp_path / "d.csv"
+    pd.DataFrame({"filename": list(emb_n.index)}).to_csv(csv_n, index=False)
+    pd.DataFrame({"filename": list(emb_d.index)}).to_csv(csv_d, index=False)
+    out = tmp_path / "csvmode"
+    out.mkdir()
+    df_avg2, df_dm2 = nomad.predict("csv", str(csv_n), str(csv_d), str(out))
+    pd.testing.assert_frame_equal(df_avg2, df_avg)
+    pd.testing.assert_frame_equal(df_dm2, df_dm)
+
+
+def test_model_call_signature_matches_reference(state_dict, golden_dir):
+    """``nomad.model(wave, lengths)`` as called at nomad.py:182, and ``lossnet_layers(wav)`` (nomad.py:143)."""
+    from nomad_b200.nomad import Nomad
+    g = np.load(os.path.join(golden_dir, "ref_small.npz"))
+    nomad = Nomad(state_dict=state_dict)
+    wav = torch.from_numpy(g["wav_b"])
+    emb = nomad.model(wav.unsqueeze(1), None)
+    assert emb.shape == (3, 256)
+    assert np.abs(emb.cpu().numpy() - g["emb_b"]).max() <= EMB_TOL
+    feats = nomad.lossnet_layers(wav.unsqueeze(1).cuda())
+    assert len(feats) == 13 and feats[0].shape == (3, 12, 768) and feats[12].shape == (3, 256)
+
+
+# ------------------------------------------------------------------------------------------ cdist
+def test_cdist_golden_and_properties(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_cdist.npz"))
+    a, b = torch.from_numpy(g["a"]).cuda(), torch.from_numpy(g["b"]).cuda()
+    dm, mean = engine.cdist_mean(a, b)
+    assert mean.dtype == torch.float64
+    assert np.abs(dm.cpu().numpy() - g["dm"]).max() <= 1e-5
+    assert np.abs(mean.cpu().numpy() - g["avg"]).max() <= 1e-5
+    _, mean_only = engine.cdist_mean(a, b, want_matrix=False)
+    np.testing.assert_allclose(mean_only.cpu().numpy(), mean.cpu().numpy(), atol=1e-12)
+    # ragged sizes around the tile edges, symmetry, zero self-distance
+    rng = np.random.default_rng(1)
+    for n, m in ((1, 1), (63, 65), (64, 64), (129, 3), (5, 1000), (1000, 899)):
+        x = rng.standard_normal((n, 256)).astype(np.float32)
+        y = rng.standard_normal((m, 256)).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True); y /= np.linalg.norm(y, axis=1, keepdims=True)
+        d, mu = engine.cdist_mean(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+        dt, _ = engine.cdist_mean(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda())
+        ref = np.sqrt(((x[:, None, :].astype(np.float64) - y[None].astype(np.float64)) ** 2).sum(-1))
+        assert np.abs(d.cpu().numpy() - ref).max() <= 1e-5
+        assert np.abs(mu.cpu().numpy() - ref.mean(1)).max() <= 1e-5
+        np.testing.assert_array_equal(d.cpu().numpy(), dt.cpu().numpy().T)
+    z, _ = engine.cdist_mean(a, a)
+    assert float(z.diagonal().abs().max()) == 0.0
+
+
+def test_cdist_full_size_properties(engine):
+    """BASELINE config 5 scale (1e5 x 1e3): checked through size-independent properties."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(100_000, 256, device="cuda", generator=g), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(1_000, 256, device="cuda", generator=g), dim=1)
+    dm, mean = engine.cdist_mean(a, b)
+    assert dm.shape == (100_000, 1_000)
+    # row mean == mean of the stored matrix rows; chord length bounds for unit vectors
+    torch.testing.assert_close(dm.double().mean(1), mean, atol=1e-6, rtol=0)
+    assert float(dm.min()) >= 0.0 and float(dm.max()) <= 2.0 + 1e-5
+    # spot rows against fp64 torch
+    idx = torch.tensor([0, 1, 63, 64, 4097, 99_999], device="cuda")
+    ref = torch.cdist(a[idx].double(), b.double())
+    assert float((dm[idx].double() - ref).abs().max()) <= 1e-5
+    # identity ||a-b||^2 = 2 - 2 a.b for unit vectors, on a checksum of all pairs
+    s = (dm.double() ** 2).sum()
+    gram = 2.0 * a.shape[0] * b.shape[0] - 2.0 * (a.double().sum(0) @ b.double().sum(0))
+    assert abs(float(s) - float(gram)) <= 1e-6 * float(gram)
+
+
+# ------------------------------------------------------------------------------ full-size embedding
+def test_full_size_batch_properties(engine, state_dict):
+    """BASELINE config 2 (256 x 4 s): unit norm, finite, batch-composition invariance, and two
+    utterances against the oracle."""
+    from oracle import w2v_oracle as O
+    B, N = 256, 64000
+    g = torch.Generator().manual_seed(0)
+    wav = 0.1 * torch.randn(B, N, generator=g)
+    emb = engine.embed_packed(wav.reshape(-1).cuda(), np.arange(B + 1, dtype=np.int64) * N)
+    e = emb.cpu().numpy()
+    assert np.isfinite(e).all()
+    np.testing.assert_allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+    sub = engine.embed([wav[5], wav[200]]).cpu().numpy()
+    np.testing.assert_array_equal(sub, e[[5, 200]])
+    with torch.no_grad():
+        ref = O.embed(state_dict, wav[[5, 200]]).numpy()
+    assert np.abs(sub - ref).max() <= EMB_TOL
+    # host-buffer entry point (H2D + D2H inside) returns the same bits
+    host = engine.embed_host(np.ascontiguousarray(wav[:8].numpy().reshape(-1)), np.arange(9, dtype=np.int64) * N)
+    np.testing.assert_array_equal(host, e[:8])
+
+
+def test_mixed_long_short_batch_against_oracle(engine, state_dict):
+    """Config-3 style ragged batch (1-20 s) incl. lengths straddling the 64-row / 128-row tile edges."""
+    from oracle import w2v_oracle as O
+    g = torch.Generator().manual_seed(3)
+    lens = [16000, 320000, 20479, 20480, 20481, 40959, 41279, 163360]
+    waves = [0.1 * torch.randn(n, generator=g) for n in lens]
+    emb = engine.embed(waves).cpu().numpy()
+    ref = O.embed_each(state_dict, waves).numpy()
+    assert np.abs(emb - ref).max() <= EMB_TOL

@@ -1,0 +1,115 @@
+"""Host-side logic of the reference-facing API that needs no GPU."""
+import os
+import wave
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from nomad_b200 import audio
+from nomad_b200.dist import shard_by_cost
+from nomad_b200.nomad import Nomad, NomadLoss, plan_batches
+
+
+def test_plan_batches_covers_everything_in_budget():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(16000, 320000, size=500).tolist()
+    batches = plan_batches(lens, 64 * 16000)
+    flat = sorted(i for b in batches for i in b)
+    assert flat == list(range(500))
+    for b in batches:
+        assert len(b) == 1 or sum(lens[i] for i in b) <= 64 * 16000
+        ls = [lens[i] for i in b]
+        assert ls == sorted(ls)  # length-bucketed
+    assert plan_batches([], 10) == []
+    assert plan_batches([5, 50, 5], 10) == [[0, 2], [1]]
+
+
+def test_shard_by_cost_balanced_and_deterministic():
+    costs = [10, 1, 1, 1, 7, 3, 3, 2]
+    s = shard_by_cost(costs, 2)
+    assert sorted(i for p in s for i in p) == list(range(8))
+    loads = [sum(costs[i] for i in p) for p in s]
+    assert abs(loads[0] - loads[1]) <= 2
+    assert s == shard_by_cost(costs, 2)
+    assert shard_by_cost([1.0], 4) == [[0], [], [], []]
+
+
+def test_load_processing_matches_torchaudio_semantics(golden_dir, tmp_path):
+    p = os.path.join(golden_dir, "wavs", "nmr-data", "MJ60_10.wav")
+    w = audio.load_processing(p)
+    assert w.dtype == torch.float32 and w.shape == (1, 27225)
+    with wave.open(p, "rb") as f:
+        pcm = np.frombuffer(f.readframes(f.getnframes()), dtype="<i2")
+    np.testing.assert_array_equal(w.numpy()[0], pcm.astype(np.float32) / 32768.0)
+    # a DataFrame row arrives as ndarray (nomad.py:194-195)
+    assert audio.load_processing(np.array([p])).shape == (1, 27225)
+    # stereo -> mean of the two channels (nomad.py:199-200); trim to 10 s (nomad.py:208-210)
+    st = tmp_path / "st.wav"
+    a = (np.arange(170000) % 2000 - 1000).astype("<i2")
+    b = (-a // 2).astype("<i2")
+    with wave.open(str(st), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(np.stack([a, b], 1).tobytes())
+    m = audio.load_processing(str(st))
+    np.testing.assert_allclose(m.numpy()[0], (a.astype(np.float32) + b.astype(np.float32)) / 2 / 32768.0, atol=1e-7)
+    assert audio.load_processing(str(st), trim=True).shape == (1, 160000)
+    # resample 8 kHz -> 16 kHz doubles the length (torchaudio.transforms.Resample, nomad.py:203-205)
+    lo = tmp_path / "lo.wav"
+    with wave.open(str(lo), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(8000)
+        f.writeframes(a[:8000].tobytes())
+    assert audio.load_processing(str(lo)).shape == (1, 16000)
+
+
+def test_predict_argument_errors_match_reference_messages(tmp_path):
+    n = Nomad.__new__(Nomad)  # argument validation happens before any device work (nomad.py:83-99)
+    with pytest.raises(Exception, match="nmr_path not specified"):
+        n.predict("dir", None, "x")
+    with pytest.raises(Exception, match="test_path not specified"):
+        n.predict("dir", "x", None)
+    with pytest.raises(Exception, match="Path to the non-matching reference files .* does not exist"):
+        n.predict("dir", str(tmp_path / "nope"), str(tmp_path))
+    with pytest.raises(Exception, match="Path to the test files .* does not exist"):
+        n.predict("dir", str(tmp_path), str(tmp_path / "nope"))
+    with pytest.raises(Exception, match="File .* does not exist"):
+        n.predict("csv", str(tmp_path / "a.csv"), str(tmp_path / "b.csv"))
+    with pytest.raises(Exception, match="Mode value wav is not valid. Valid values are dir and csv"):
+        n.predict("wav", str(tmp_path), str(tmp_path))
+    bad = tmp_path / "bad.csv"
+    pd.DataFrame({"path": ["a.wav"]}).to_csv(bad, index=False)
+    with pytest.raises(Exception, match="not including a column called filename"):
+        n.get_embeddings(str(bad))
+
+
+def test_write_results_reproduces_reference_csv(golden_dir, tmp_path):
+    """Feeding the reference's own unrounded matrix through our frame/CSV writer gives its CSV bytes."""
+    g = np.load(os.path.join(golden_dir, "ref_predict.npz"))
+    n = Nomad.__new__(Nomad)
+    deg = ["/some/dir/" + f for f in g["deg_files"]]
+    nmr = ["/other/" + f for f in g["nmr_files"]]
+    df_avg, df_dm = n.write_results(deg, nmr, g["dm"], g["avg"], str(tmp_path))
+    assert open(tmp_path / "nomad_avg.csv").read() == str(g["csv_avg"])
+    assert open(tmp_path / "nomad_scores.csv").read() == str(g["csv_scores"])
+    assert list(df_avg.index) == list(g["df_avg_index"]) and df_avg.index.name == "Test File"
+    assert list(df_dm.columns) == list(g["df_dm_columns"])
+    np.testing.assert_array_equal(df_dm.to_numpy(), g["df_dm_values"])
+    np.testing.assert_array_equal(df_avg["NOMAD"].to_numpy(), g["df_avg_values"])
+    # default location: results-csv/<DD-MM-YYYY_HH-MM-SS>/<ts>_nomad_{avg,scores}.csv (nomad.py:123-133)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        n.write_results(deg, nmr, g["dm"], g["avg"], None)
+        (d,) = os.listdir("results-csv")
+        assert sorted(os.listdir(os.path.join("results-csv", d))) == [f"{d}_nomad_avg.csv", f"{d}_nomad_scores.csv"]
+    finally:
+        os.chdir(cwd)
+
+
+def test_nomad_loss_module_matches_reference_formula():
+    torch.manual_seed(0)
+    ref = [torch.randn(2, 5, 8) for _ in range(12)] + [torch.randn(2, 4)]
+    tst = [torch.randn(2, 5, 8) for _ in range(12)] + [torch.randn(2, 4)]
+    exp = sum(torch.nn.functional.l1_loss(t, r) for r, t in zip(ref, tst))
+    assert torch.allclose(NomadLoss()(ref, tst), exp)
