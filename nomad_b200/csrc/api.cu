@@ -58,7 +58,7 @@ int make_plan(const int64_t* off, int B, Plan* p) {
     return 0;
 }
 
-size_t carve_workspace(const Plan& p, void* base, Workspace* ws) {
+size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
         size_t at = o;
@@ -66,19 +66,52 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws) {
         return base ? (void*)((char*)base + at) : nullptr;
     };
     Workspace w;
+    memset(&w, 0, sizeof(w));
+    w.save = save;
+    const size_t F = (size_t)p.frames;
     w.meta = (UttMeta*)take(sizeof(UttMeta) * p.B);
     w.stat_part = (double*)take(sizeof(double) * NSTAT * p.max_chunks * p.B);
     w.c0_fold = (float*)take(sizeof(float) * 12 * CONV_DIM * p.B);
-    w.act_a = (op_t*)take(2ull * CONV_DIM * (p.rows0 + 8));
-    w.act_b = (op_t*)take(2ull * CONV_DIM * (p.rows0 / 2 + 8));
-    w.x = (float*)take(4ull * EMBED * p.frames);
-    w.xh = (op_t*)take(2ull * EMBED * p.frames);
-    w.pre = (float*)take(4ull * EMBED * p.frames);
+    w.gn_stat = save ? (float*)take(sizeof(float) * 2 * CONV_DIM * p.B) : nullptr;
+    if (!save) {
+        op_t* act_a = (op_t*)take(2ull * CONV_DIM * (p.rows0 + 8));
+        op_t* act_b = (op_t*)take(2ull * CONV_DIM * (p.rows0 / 2 + 8));
+        for (int l = 0; l < 7; ++l) {
+            w.y[l] = (l & 1) ? act_b : act_a;
+            w.aux[l] = nullptr;
+        }
+        w.ln0_out = act_b;  // level 6 lives in act_a
+    } else {
+        for (int l = 0; l < 7; ++l) {
+            w.y[l] = (op_t*)take(2ull * CONV_DIM * ((p.rows0 >> l) + 8));
+            w.aux[l] = (op_t*)take(2ull * CONV_DIM * ((p.rows0 >> l) + 8));
+        }
+        w.ln0_out = (op_t*)take(2ull * CONV_DIM * (F + 8));
+    }
+    w.x = (float*)take(4ull * EMBED * F);
+    w.xh = (op_t*)take(2ull * EMBED * F);
     w.pos_g = (op_t*)take(2ull * POS_G * POS_GC * (p.pos_rows + POS_K));
     w.pos_y = (op_t*)take(2ull * EMBED * p.pos_rows);
-    w.qkv = (op_t*)take(2ull * 3 * EMBED * p.frames);
-    w.attn = (op_t*)take(2ull * EMBED * p.frames);
-    w.ffn_h = (op_t*)take(2ull * FFN * p.frames);
+    w.pos_aux = save ? (op_t*)take(2ull * EMBED * p.pos_rows) : nullptr;
+    w.ffn_h = (op_t*)take(2ull * FFN * F);
+    if (!save) {
+        float* pre = (float*)take(4ull * EMBED * F);
+        op_t* qkv = (op_t*)take(2ull * 3 * EMBED * F);
+        op_t* attn = (op_t*)take(2ull * EMBED * F);
+        w.x0 = pre;
+        for (int l = 0; l < LAYERS; ++l) w.layer[l] = LayerBufs{qkv, attn, nullptr, pre, nullptr, pre};
+    } else {
+        w.x0 = (float*)take(4ull * EMBED * F);
+        for (int l = 0; l < LAYERS; ++l) {
+            LayerBufs& L = w.layer[l];
+            L.qkv = (op_t*)take(2ull * 3 * EMBED * F);
+            L.attn = (op_t*)take(2ull * EMBED * F);
+            L.lse = (float*)take(4ull * HEADS * F);
+            L.pre1 = (float*)take(4ull * EMBED * F);
+            L.ffn_aux = (op_t*)take(2ull * FFN * F);
+            L.pre2 = (float*)take(4ull * EMBED * F);
+        }
+    }
     w.bytes = o;
     if (ws) *ws = w;
     return o;
@@ -145,6 +178,13 @@ static int build_weights(Handle* h, TensorTable& tt) {
     NB_TRY(upload_f32(h, gnb, 512, &w.gn_b));
     w.conv_w[0] = nullptr;
     w.conv_wt[0] = nullptr;
+    for (int l = 0; l < 7; ++l) w.conv_wte[l] = nullptr;
+    {
+        std::vector<op_t> t((size_t)16 * 512, f2op(0.f));
+        for (int c = 0; c < 512; ++c)
+            for (int j = 0; j < 10; ++j) t[(size_t)j * 512 + c] = f2op(c0[c * 10 + j]);
+        NB_TRY(upload(h, t, &w.conv0_wh));
+    }
     for (int l = 1; l < 7; ++l) {
         const int k = CONV_KERNEL[l];
         GET(cw, P + "feature_extractor.conv_layers." + std::to_string(l) + ".0.weight", 512LL * 512 * k);
@@ -159,6 +199,15 @@ static int build_weights(Handle* h, TensorTable& tt) {
                 }
         NB_TRY(upload(h, fw, &w.conv_w[l]));
         NB_TRY(upload(h, bw, &w.conv_wt[l]));
+        if (k == 3) {
+            std::vector<op_t> ew((size_t)512 * 1024);
+            for (int c = 0; c < 512; ++c)
+                for (int o = 0; o < 512; ++o) {
+                    ew[(size_t)c * 1024 + o] = f2op(cw[((size_t)o * 512 + c) * 3 + 2]);
+                    ew[(size_t)c * 1024 + 512 + o] = f2op(cw[((size_t)o * 512 + c) * 3 + 0]);
+                }
+            NB_TRY(upload(h, ew, &w.conv_wte[l]));
+        }
     }
     GET(l0g, P + "layer_norm.weight", 512);
     GET(l0b, P + "layer_norm.bias", 512);
@@ -282,7 +331,7 @@ static int build_weights(Handle* h, TensorTable& tt) {
 // Forward pass
 static constexpr int META_SLOTS = 4;
 
-static int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st) {
+int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st) {
     static thread_local int slot = 0;
     if (h->meta_cap < p.B) {
         if (h->meta_host) {
@@ -308,7 +357,7 @@ static int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st) 
     return 0;
 }
 
-static GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld) {
+GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld) {
     GemmEpilogue e;
     memset(&e, 0, sizeof(e));
     e.flags = flags;
@@ -322,78 +371,91 @@ static GemmEpilogue epi_linear(int flags, const float* bias, const float* resid,
 }
 
 // wav (device, packed) -> residual stream after the 12th layer (ws.x), optionally the 12 layer outputs.
-static int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st,
-                           float* layers_out, int layer_T) {
+int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st,
+                    float* layers_out, int layer_T) {
     const Weights& w = h->w;
     const int impl = h->gemm_impl;
     const long long F = p.frames;
+    const bool save = ws.save;
     // conv0 + GroupNorm + GELU
     NB_TRY(launch_wave_stats(st, wav, ws.meta, p.B, p.max_chunks, ws.stat_part));
-    NB_TRY(launch_gn_fold(st, ws.stat_part, ws.meta, p.B, p.max_chunks, w.conv0_w, w.gn_g, w.gn_b, ws.c0_fold));
-    NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, p.rows0, ws.c0_fold, ws.act_a));
+    NB_TRY(launch_gn_fold(st, ws.stat_part, ws.meta, p.B, p.max_chunks, w.conv0_w, w.gn_g, w.gn_b, ws.c0_fold,
+                          ws.gn_stat));
+    NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, p.rows0, ws.c0_fold, ws.y[0], ws.aux[0]));
     // conv 1..6 as overlapping-row GEMMs over the flat channels-last activation
-    op_t* in = ws.act_a;
-    op_t* out = ws.act_b;
     for (int l = 1; l < 7; ++l) {
         const long long M = p.rows0 >> l;
-        GemmOperand A{in, M, 2 * CONV_DIM, 0, 0};
+        GemmOperand A{ws.y[l - 1], M, 2 * CONV_DIM, 0, 0};
         GemmOperand Bw{w.conv_w[l], CONV_DIM, (long long)CONV_KERNEL[l] * CONV_DIM, 0, 0};
-        GemmEpilogue e = epi_linear(EPI_GELU | EPI_OUT_H16, nullptr, nullptr, nullptr, out, CONV_DIM);
+        GemmEpilogue e = epi_linear(EPI_GELU | EPI_OUT_H16, nullptr, nullptr, nullptr, ws.y[l], CONV_DIM);
+        if (save) {
+            e.flags |= EPI_SAVE_DGELU;
+            e.aux_out = ws.aux[l];
+        }
         NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, CONV_KERNEL[l] * CONV_DIM, 1, e, impl));
-        op_t* t = in; in = out; out = t;
+        if (save) NB_TRY(launch_zero_pad_rows(st, ws.aux[l], ws.meta, p.B, l));
     }
-    // now `in` holds level 6 (frames x 512); LayerNorm(512) -> `out`; projection -> ws.pre (x0)
-    NB_TRY(launch_ln512(st, in, F, w.ln0_g, w.ln0_b, out));
+    // LayerNorm(512) -> projection -> x0
+    NB_TRY(launch_ln512(st, ws.y[6], F, w.ln0_g, w.ln0_b, ws.ln0_out));
     {
-        GemmOperand A{out, F, CONV_DIM, 0, 0};
+        GemmOperand A{ws.ln0_out, F, CONV_DIM, 0, 0};
         GemmOperand Bw{w.proj_w, EMBED, CONV_DIM, 0, 0};
-        GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_F32, w.proj_b, nullptr, ws.pre, nullptr, EMBED);
+        GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_F32, w.proj_b, nullptr, ws.x0, nullptr, EMBED);
         NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, CONV_DIM, 1, e, impl));
     }
     // positional conv (grouped, k = 128) as 16 overlapping-row GEMMs + residual + encoder LayerNorm
     {
         const long long rows_alloc = p.pos_rows + POS_K;
         NB_CUDA(cudaMemsetAsync(ws.pos_g, 0, 2ull * POS_G * POS_GC * rows_alloc, st));
-        NB_TRY(launch_pos_scatter(st, ws.pre, ws.meta, p.B, F, rows_alloc, ws.pos_g));
+        NB_TRY(launch_pos_scatter(st, ws.x0, ws.meta, p.B, F, rows_alloc, ws.pos_g));
         GemmOperand A{ws.pos_g, p.pos_rows, POS_GC, rows_alloc * POS_GC, 0};
         GemmOperand Bw{w.pos_w, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
         GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, w.pos_b, nullptr, nullptr, ws.pos_y, EMBED);
         e.bias_bstride = POS_GC;
         e.out_bstride = POS_GC;
+        if (save) {
+            e.flags |= EPI_SAVE_DGELU;
+            e.aux_out = ws.pos_aux;
+        }
         NB_TRY(gemm_h16(st, A, Bw, (int)p.pos_rows, POS_GC, POS_K * POS_GC, POS_G, e, impl));
-        NB_TRY(launch_pos_finish_ln(st, ws.pre, ws.pos_y, ws.meta, p.B, F, w.lne_g, w.lne_b, ws.x, ws.xh));
+        NB_TRY(launch_pos_finish_ln(st, ws.x0, ws.pos_y, ws.meta, p.B, F, w.lne_g, w.lne_b, ws.x, ws.xh));
     }
-    NB_CUDA(cudaMemsetAsync(ws.attn, 0, 2ull * EMBED * F, st));
     for (int l = 0; l < LAYERS; ++l) {
         const LayerWeights& L = w.layer[l];
+        const LayerBufs& Lb = ws.layer[l];
+        if (l == 0 || save) NB_CUDA(cudaMemsetAsync(Lb.attn, 0, 2ull * EMBED * F, st));  // padded rows stay finite
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_qkv, 3 * EMBED, EMBED, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_H16, L.b_qkv, nullptr, nullptr, ws.qkv, 3 * EMBED);
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_H16, L.b_qkv, nullptr, nullptr, Lb.qkv, 3 * EMBED);
             NB_TRY(gemm_h16(st, A, Bw, (int)F, 3 * EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_attention(st, ws.qkv, ws.meta, p.B, p.max_T, ws.attn));
+        NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse));
         {
-            GemmOperand A{ws.attn, F, EMBED, 0, 0};
+            GemmOperand A{Lb.attn, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_o, EMBED, EMBED, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_o, ws.x, ws.pre, nullptr, EMBED);
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_o, ws.x, Lb.pre1, nullptr, EMBED);
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_ln768(st, ws.pre, ws.meta, p.B, F, L.ln1_g, L.ln1_b, ws.x, ws.xh, nullptr, 0));
+        NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, p.B, F, L.ln1_g, L.ln1_b, ws.x, ws.xh, nullptr, 0));
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_fc1, FFN, EMBED, 0, 0};
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, L.b_fc1, nullptr, nullptr, ws.ffn_h, FFN);
+            if (save) {
+                e.flags |= EPI_SAVE_DGELU;
+                e.aux_out = Lb.ffn_aux;
+            }
             NB_TRY(gemm_h16(st, A, Bw, (int)F, FFN, EMBED, 1, e, impl));
         }
         {
             GemmOperand A{ws.ffn_h, F, FFN, 0, 0};
             GemmOperand Bw{L.w_fc2, EMBED, FFN, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_fc2, ws.x, ws.pre, nullptr, EMBED);
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_fc2, ws.x, Lb.pre2, nullptr, EMBED);
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, FFN, 1, e, impl));
         }
         float* lo = layers_out ? layers_out + (size_t)l * p.B * layer_T * EMBED : nullptr;
-        NB_TRY(launch_ln768(st, ws.pre, ws.meta, p.B, F, L.ln2_g, L.ln2_b, ws.x, ws.xh, lo, layer_T));
+        NB_TRY(launch_ln768(st, Lb.pre2, ws.meta, p.B, F, L.ln2_g, L.ln2_b, ws.x, ws.xh, lo, layer_T));
     }
     return 0;
 }
@@ -407,9 +469,6 @@ static int check_handle(const nomad_b200_handle* hh) {
 
 using namespace nb;
 
-struct nomad_b200_handle {
-    nb::Handle h;
-};
 
 extern "C" {
 
@@ -485,7 +544,7 @@ int nomad_b200_set_loss_head(nomad_b200_handle* hh, const float* w, const float*
 size_t nomad_b200_embed_workspace_bytes(const int64_t* sample_offsets, int B) {
     Plan p;
     if (make_plan(sample_offsets, B, &p)) return 0;
-    return carve_workspace(p, nullptr, nullptr);
+    return carve_workspace(p, nullptr, nullptr, false);
 }
 
 int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
@@ -499,7 +558,7 @@ int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t*
     // wav_dev points at sample sample_offsets[0]
     for (auto& m : p.utt) m.wav_off -= sample_offsets[0];
     Workspace ws;
-    const size_t need = carve_workspace(p, workspace_dev, &ws);
+    const size_t need = carve_workspace(p, workspace_dev, &ws, false);
     NB_CHECK(workspace_bytes >= need, "embed: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "embed: workspace must be 1024-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -520,7 +579,7 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
     // the tail of the caller's workspace holds the staged waveform and the embeddings
     Plan p;
     NB_TRY(make_plan(sample_offsets, B, &p));
-    const size_t core = carve_workspace(p, nullptr, nullptr);
+    const size_t core = carve_workspace(p, nullptr, nullptr, false);
     const size_t wav_bytes = align_up((size_t)total * 4 + 64, 1024), emb_bytes = align_up((size_t)B * EMB * 4, 1024);
     NB_CHECK(workspace_bytes >= core + wav_bytes + emb_bytes,
              "embed_host: workspace too small (%zu < %zu bytes; embed_workspace_bytes + 4*samples + 1024*B + 4096)",
@@ -567,7 +626,7 @@ int nomad_b200_layers_fwd(nomad_b200_handle* hh, const float* wav_dev, int B, in
     Plan p;
     NB_TRY(make_plan(off.data(), B, &p));
     Workspace ws;
-    const size_t need = carve_workspace(p, workspace_dev, &ws);
+    const size_t need = carve_workspace(p, workspace_dev, &ws, false);
     NB_CHECK(workspace_bytes >= need, "layers_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
     NB_TRY(upload_meta(h, p, ws.meta, st));
@@ -615,20 +674,6 @@ int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nm
     NB_CUDA(cudaMemcpyAsync(row_mean_host, rm_d, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
     return 0;
-}
-
-size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
-    (void)B; (void)N; (void)with_grad;
-    return 0;
-}
-
-int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const float* clean_dev, int B, int64_t N,
-                            float feature_grad_mult, float* loss_dev, float* d_est_dev, void* workspace_dev,
-                            size_t workspace_bytes, void* stream) {
-    (void)hh; (void)est_dev; (void)clean_dev; (void)B; (void)N; (void)feature_grad_mult; (void)loss_dev;
-    (void)d_est_dev; (void)workspace_dev; (void)workspace_bytes; (void)stream;
-    set_error("loss_fwd_bwd: not implemented yet");
-    return 1;
 }
 
 }  // extern "C"

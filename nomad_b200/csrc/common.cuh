@@ -86,6 +86,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float e = fmaf(-p, __expf(-z * z), 1.0f);
     return fmaf(0.5f * ax, e, 0.5f * x);
 }
+// gelu(x) and d gelu / dx = Phi(x) + x phi(x) from one erf / one exp evaluation
+__device__ __forceinline__ float gelu_erf_with_grad(float x, float& grad) {
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float ex = __expf(-z * z);          // exp(-x^2 / 2)
+    const float e = fmaf(-p, ex, 1.0f);       // erf(|x| / sqrt 2)
+    const float cdf = 0.5f + copysignf(0.5f * e, x);
+    grad = fmaf(x * 0.39894228040143267794f, ex, cdf);
+    return fmaf(0.5f * ax, e, 0.5f * x);
+}
 // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

@@ -215,7 +215,7 @@ __device__ __forceinline__ void load_tile_async(op_t* tile, const op_t* __restri
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__ qkv, const UttMeta* __restrict__ meta,
-                                                        op_t* __restrict__ out) {
+                                                        op_t* __restrict__ out, float* __restrict__ lse) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
     const int T = meta[b].T;
     const int q0 = qt * ATT_BQ;
@@ -330,6 +330,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__
     }
     const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    if (lse != nullptr && (lane & 3) == 0) {
+        if (r0 < T) lse[(f0 + r0) * HEADS + h] = m_run[0] + __logf(l_run[0]);
+        if (r1 < T) lse[(f0 + r1) * HEADS + h] = m_run[1] + __logf(l_run[1]);
+    }
     op_t* ob = out + f0 * EMBED + h * HEAD_DIM + 2 * (lane & 3);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -338,9 +342,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__
     }
 }
 
-int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out) {
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse) {
     dim3 grid((max_T + ATT_BQ - 1) / ATT_BQ, HEADS, B);
-    attention_kernel<<<grid, 128, 0, st>>>(qkv, meta, out);
+    attention_kernel<<<grid, 128, 0, st>>>(qkv, meta, out, lse);
     NB_LAUNCHED();
     return 0;
 }

@@ -67,7 +67,8 @@ int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, in
 __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__ part,
                                                       const UttMeta* __restrict__ meta, int max_chunks,
                                                       const float* __restrict__ w0, const float* __restrict__ gn_g,
-                                                      const float* __restrict__ gn_b, float* __restrict__ fold) {
+                                                      const float* __restrict__ gn_b, float* __restrict__ fold,
+                                                      float* __restrict__ stat_out) {
     const int b = blockIdx.x;
     const UttMeta m = meta[b];
     __shared__ double s[NSTAT];
@@ -102,12 +103,16 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
 #pragma unroll
     for (int j = 0; j < 10; ++j) o[j] = (float)(w[j] * a);
     o[10] = (float)((double)gn_b[c] - mean * a);
-    o[11] = 0.f;
+    o[11] = (float)a;  // gamma * rstd, folded into the saved GELU gradient for the loss backward
+    if (stat_out != nullptr) {
+        stat_out[((long long)b * CONV_DIM + c) * 2 + 0] = (float)mean;
+        stat_out[((long long)b * CONV_DIM + c) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
 }
 
 int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
-                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold) {
-    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold);
+                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out) {
+    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold, stat_out);
     NB_LAUNCHED();
     return 0;
 }
@@ -120,7 +125,8 @@ static constexpr int C0_ROWS = 64;
 
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav,
                                                           const UttMeta* __restrict__ meta, int B,
-                                                          const float* __restrict__ fold, op_t* __restrict__ out) {
+                                                          const float* __restrict__ fold, op_t* __restrict__ out,
+                                                          op_t* __restrict__ aux_out) {
     const int row_base = blockIdx.x * C0_ROWS;
     // utterance lookup: frame-level offsets are row offsets / 64
     const int b = find_utt_by_frame(meta, B, blockIdx.x);
@@ -133,39 +139,81 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
         xs[i] = (s < m.n) ? __ldg(x + s) : 0.f;
     }
     const int c = 2 * threadIdx.x;
-    float w0[11], w1[11];
+    float w0[12], w1[12];
     {
         const float4* f = reinterpret_cast<const float4*>(fold + ((long long)b * CONV_DIM + c) * 12);
         const float4 a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3), a4 = __ldg(f + 4),
                      a5 = __ldg(f + 5);
         w0[0] = a0.x; w0[1] = a0.y; w0[2] = a0.z; w0[3] = a0.w; w0[4] = a1.x; w0[5] = a1.y; w0[6] = a1.z;
-        w0[7] = a1.w; w0[8] = a2.x; w0[9] = a2.y; w0[10] = a2.z;
+        w0[7] = a1.w; w0[8] = a2.x; w0[9] = a2.y; w0[10] = a2.z; w0[11] = a2.w;
         w1[0] = a3.x; w1[1] = a3.y; w1[2] = a3.z; w1[3] = a3.w; w1[4] = a4.x; w1[5] = a4.y; w1[6] = a4.z;
-        w1[7] = a4.w; w1[8] = a5.x; w1[9] = a5.y; w1[10] = a5.z;
+        w1[7] = a4.w; w1[8] = a5.x; w1[9] = a5.y; w1[10] = a5.z; w1[11] = a5.w;
     }
     __syncthreads();
     uint32_t* o = reinterpret_cast<uint32_t*>(out + (long long)row_base * CONV_DIM + c);
     const int valid = m.T0 - t_base;  // rows of this block that are real frames
+    if (aux_out == nullptr) {
 #pragma unroll 4
-    for (int t = 0; t < C0_ROWS; ++t) {
-        uint32_t packed = 0u;
-        if (t < valid) {
-            float y0 = w0[10], y1 = w1[10];
+        for (int t = 0; t < C0_ROWS; ++t) {
+            uint32_t packed = 0u;
+            if (t < valid) {
+                float y0 = w0[10], y1 = w1[10];
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const float xv = xs[5 * t + j];
-                y0 = fmaf(w0[j], xv, y0);
-                y1 = fmaf(w1[j], xv, y1);
+                for (int j = 0; j < 10; ++j) {
+                    const float xv = xs[5 * t + j];
+                    y0 = fmaf(w0[j], xv, y0);
+                    y1 = fmaf(w1[j], xv, y1);
+                }
+                packed = pack_op(gelu_erf(y0), gelu_erf(y1));
             }
-            packed = pack_op(gelu_erf(y0), gelu_erf(y1));
+            o[(long long)t * (CONV_DIM / 2)] = packed;
         }
-        o[(long long)t * (CONV_DIM / 2)] = packed;
+    } else {
+        uint32_t* ao = reinterpret_cast<uint32_t*>(aux_out + (long long)row_base * CONV_DIM + c);
+#pragma unroll 2
+        for (int t = 0; t < C0_ROWS; ++t) {
+            uint32_t packed = 0u, gpacked = 0u;
+            if (t < valid) {
+                float y0 = w0[10], y1 = w1[10];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const float xv = xs[5 * t + j];
+                    y0 = fmaf(w0[j], xv, y0);
+                    y1 = fmaf(w1[j], xv, y1);
+                }
+                float g0, g1;
+                y0 = gelu_erf_with_grad(y0, g0);
+                y1 = gelu_erf_with_grad(y1, g1);
+                packed = pack_op(y0, y1);
+                gpacked = pack_op(g0 * w0[11], g1 * w1[11]);
+            }
+            o[(long long)t * (CONV_DIM / 2)] = packed;
+            ao[(long long)t * (CONV_DIM / 2)] = gpacked;
+        }
     }
 }
 
+// rows [T_l, rows_l) of each utterance at conv level l := 0
+__global__ void __launch_bounds__(256) zero_pad_rows_kernel(op_t* __restrict__ buf, const UttMeta* __restrict__ meta,
+                                                            int level) {
+    const UttMeta m = meta[blockIdx.x];
+    int T = m.T0;
+    for (int l = 1; l <= level; ++l) T = (T - (l < 5 ? 3 : 2)) / 2 + 1;
+    const long long r0 = ((long long)m.row0 >> level) + T, r1 = ((long long)m.row0 + m.rows0) >> level;
+    uint4* p = reinterpret_cast<uint4*>(buf + r0 * CONV_DIM);
+    const long long n = (r1 - r0) * (CONV_DIM / 8);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B, int level) {
+    zero_pad_rows_kernel<<<B, 256, 0, st>>>(buf, meta, level);
+    NB_LAUNCHED();
+    return 0;
+}
+
 int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
-                       const float* fold, op_t* out) {
-    conv0_apply_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, out);
+                       const float* fold, op_t* out, op_t* aux_out) {
+    conv0_apply_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, out, aux_out);
     NB_LAUNCHED();
     return 0;
 }

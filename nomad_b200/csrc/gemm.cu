@@ -50,11 +50,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    if (flags & EPI_GELU) {
+    const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
+    if (flags & EPI_SAVE_DGELU) {
+        uint4* gp = reinterpret_cast<uint4*>(e.aux_out + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] = gelu_erf_with_grad(v[8 * j + i], g[i]);
+            if (j * 8 < ncols)
+                gp[j] = make_uint4(pack_op(g[0], g[1]), pack_op(g[2], g[3]), pack_op(g[4], g[5]), pack_op(g[6], g[7]));
+        }
+    } else if (flags & EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
-    const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     if (flags & EPI_MUL_AUX) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
 #pragma unroll
@@ -107,8 +117,14 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, 
         return;
     }
     if (flags & EPI_BIAS) v += e.bias[(long long)b * e.bias_bstride + col];
-    if (flags & EPI_GELU) v = gelu_erf(v);
     const long long off = row * e.ldo + col + (long long)b * e.out_bstride;
+    if (flags & EPI_SAVE_DGELU) {
+        float g;
+        v = gelu_erf_with_grad(v, g);
+        e.aux_out[off] = f2op(g);
+    } else if (flags & EPI_GELU) {
+        v = gelu_erf(v);
+    }
     if (flags & EPI_MUL_AUX) v *= op2f(e.aux[off]);
     if (flags & EPI_RESID) v += e.resid[row * e.ldr + col + (long long)b * e.resid_bstride];
     if (flags & EPI_OUT_F32) e.out_f[off] = v;

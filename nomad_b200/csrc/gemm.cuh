@@ -13,7 +13,8 @@ enum : int {
     EPI_OUT_F32 = 8,   // store fp32
     EPI_OUT_H16 = 16, // store op_t
     EPI_MUL_AUX = 32,  // * aux[row, col] (op_t)  -- dgrad through GELU: aux holds gelu'(pre-activation)
-    EPI_CDIST = 64,    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
+    EPI_CDIST = 64,
+    EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
 };
 
 // One operand: ``rows`` rows of K op_t values, row r of batch b starting at
@@ -38,7 +39,8 @@ struct GemmEpilogue {
     const float* resid;       // fp32, element (row, col) at resid[row * ldr + col + b * resid_bstride]
     long long ldr;
     long long resid_bstride;
-    const op_t* aux;          // op_t, same indexing as out (ldo / out_bstride)
+    const op_t* aux;          // 16-bit, same indexing as out (ldo / out_bstride)
+    op_t* aux_out;            // EPI_SAVE_DGELU target, same indexing as out
     float* out_f;             // element (row, col) of batch b at out[row * ldo + col + b * out_bstride]
     op_t* out_h;
     long long ldo;

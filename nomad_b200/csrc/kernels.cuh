@@ -7,9 +7,11 @@ namespace nb {
 // ---- frontend.cu: waveform -> conv0 + GroupNorm + GELU, LayerNorm(512)
 int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int B, int max_chunks, double* part);
 int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
-                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold);
+                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out);
 int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
-                       const float* fold, op_t* out);
+                       const float* fold, op_t* out, op_t* aux_out);
+// zero rows [T_l, rows_l) of every utterance at conv level l (so masked rows carry no gradient)
+int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B, int level);
 int launch_ln512(cudaStream_t st, const op_t* in, long long rows, const float* g, const float* b, op_t* out);
 
 // ---- encoder.cu
@@ -22,7 +24,7 @@ int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, co
 // layer_out[(utt * T + t) * 768 + c] for a uniform batch
 int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
                  const float* b, float* x, op_t* xh, float* layer_out, int layer_T);
-int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out);
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse);
 int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
                      const float* head_b, float* emb, float* pooled_out);
 

@@ -48,6 +48,8 @@ struct Weights {
     float *gn_g, *gn_b;  // [512]
     op_t* conv_w[7];     // l = 1..6: [512][k*512], K index = tap*512 + cin
     op_t* conv_wt[7];    // dgrad: [k][cin=512][cout=512] -> per tap [N'=cin][K'=cout]
+    op_t* conv_wte[7];   // dgrad of the even input rows of the k=3 layers: [cin][tap2: cout | tap0: cout]
+    op_t* conv0_wh;      // conv0 dgrad: [16][512] = w0[c][j] transposed, rows 10..15 zero
     float *ln0_g, *ln0_b;  // LayerNorm(512)
     op_t* proj_w;        // [768][512]
     op_t* proj_wt;       // [512][768]
@@ -76,21 +78,35 @@ struct Plan {
     bool uniform = false;  // all utterances the same length
 };
 
-// Device pointers carved from the caller's workspace for one forward pass.
+// Device pointers carved from the caller's workspace for one forward pass.  In scoring mode the conv
+// levels ping-pong between two buffers and the per-layer pointers alias shared scratch; in "save" mode
+// (loss path) every tensor the backward needs gets its own storage.
+struct LayerBufs {
+    op_t* qkv;      // frames x 2304
+    op_t* attn;     // frames x 768 (attention output O)
+    float* lse;     // frames x 12 log-sum-exp of the attention rows (save mode) or nullptr
+    float* pre1;    // frames x 768: x_in + out_proj(attn)        (input of self_attn_layer_norm)
+    op_t* ffn_aux;  // frames x 3072: gelu'(fc1 pre-activation)   (save mode) or nullptr
+    float* pre2;    // frames x 768: x1 + fc2(h)                   (input of final_layer_norm)
+};
+
 struct Workspace {
+    bool save;
     UttMeta* meta;       // [B]
     double* stat_part;   // [B][max_chunks][65]
-    float* c0_fold;      // [B][512][12]: 10 folded taps, shift, pad
-    op_t* act_a;         // level 0/2/4/6: (rows0 + 8) x 512
-    op_t* act_b;         // level 1/3/5 and LN(512) output: (rows0/2 + 8) x 512
-    float* x;            // residual stream, frames x 768 fp32
-    op_t* xh;            // op_t copy (GEMM operand)
-    float* pre;          // pre-LayerNorm sums, frames x 768 fp32
+    float* c0_fold;      // [B][512][12]: 10 folded taps, shift, gamma * rstd
+    float* gn_stat;      // save mode: [B][512][2] mean and rstd of the raw conv0 output per (utt, channel)
+    op_t* y[7];          // conv level outputs, level l: (rows0 >> l) + 8 rows x 512
+    op_t* aux[7];        // save mode: gelu'(pre-activation) per level (level 0: times gamma * rstd)
+    op_t* ln0_out;       // LayerNorm(512) output, frames x 512
+    float* x0;           // feature projection output, frames x 768 fp32
     op_t* pos_g;         // [16][pos_rows + 128][48]
-    op_t* pos_y;         // [pos_rows][768]
-    op_t* qkv;           // frames x 2304
-    op_t* attn;          // frames x 768
+    op_t* pos_y;         // [pos_rows][768] GELU(pos conv)
+    op_t* pos_aux;       // save mode: gelu' of the pos conv pre-activation, [pos_rows][768]
+    float* x;            // residual stream, frames x 768 fp32
+    op_t* xh;            // 16-bit copy (GEMM operand)
     op_t* ffn_h;         // frames x 3072
+    LayerBufs layer[LAYERS];
     size_t bytes;
 };
 
@@ -106,6 +122,14 @@ struct Handle {
 };
 
 int make_plan(const int64_t* sample_offsets, int B, Plan* plan);
-size_t carve_workspace(const Plan& p, void* base, Workspace* ws);
+size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save);
+int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st, float* layers_out,
+                    int layer_T);
+int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st);
+GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld);
 
 }  // namespace nb
+
+struct nomad_b200_handle {
+    nb::Handle h;
+};
