@@ -408,16 +408,21 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
         const long long rows_alloc = p.pos_rows + POS_K;
         NB_CUDA(cudaMemsetAsync(ws.pos_g, 0, 2ull * POS_G * POS_GC * rows_alloc, st));
         NB_TRY(launch_pos_scatter(st, ws.x0, ws.meta, p.B, F, rows_alloc, ws.pos_g));
-        GemmOperand A{ws.pos_g, p.pos_rows, POS_GC, rows_alloc * POS_GC, 0};
-        GemmOperand Bw{w.pos_w, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
-        GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, w.pos_b, nullptr, nullptr, ws.pos_y, EMBED);
-        e.bias_bstride = POS_GC;
-        e.out_bstride = POS_GC;
-        if (save) {
-            e.flags |= EPI_SAVE_DGELU;
-            e.aux_out = ws.pos_aux;
+        if (impl == 0) {
+            NB_TRY(launch_posconv(st, ws.pos_g, rows_alloc, p.pos_rows, w.pos_w, w.pos_b,
+                                  EPI_BIAS | EPI_GELU | (save ? EPI_SAVE_DGELU : 0), ws.pos_y, ws.pos_aux));
+        } else {  // cross-check path: the same conv through the generic overlapping-row GEMM
+            GemmOperand A{ws.pos_g, p.pos_rows, POS_GC, rows_alloc * POS_GC, 0};
+            GemmOperand Bw{w.pos_w, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, w.pos_b, nullptr, nullptr, ws.pos_y, EMBED);
+            e.bias_bstride = POS_GC;
+            e.out_bstride = POS_GC;
+            if (save) {
+                e.flags |= EPI_SAVE_DGELU;
+                e.aux_out = ws.pos_aux;
+            }
+            NB_TRY(gemm_h16(st, A, Bw, (int)p.pos_rows, POS_GC, POS_K * POS_GC, POS_G, e, impl));
         }
-        NB_TRY(gemm_h16(st, A, Bw, (int)p.pos_rows, POS_GC, POS_K * POS_GC, POS_G, e, impl));
         NB_TRY(launch_pos_finish_ln(st, ws.x0, ws.pos_y, ws.meta, p.B, F, w.lne_g, w.lne_b, ws.x, ws.xh));
     }
     for (int l = 0; l < LAYERS; ++l) {

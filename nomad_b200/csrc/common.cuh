@@ -69,38 +69,52 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float gelu_erf_exact(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~10 FMA instead of
-// libdevice erff's ~30 instructions.  gelu(x) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2).
+// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~12 FMA-pipe
+// instructions instead of libdevice erff's ~30.  With y = |x| sqrt(log2(e) / 2):
+//   exp(-x^2/2) = 2^(-y^2),  t = 1 / (1 + p |x| / sqrt 2) = 1 / (1 + P y),  erf = 1 - poly(t) 2^(-y^2)
+//   gelu(x) = 0.5 (x + |x| erf(|x| / sqrt 2))
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define NB_GELU_K1 0.84932180028801904272f  /* sqrt(log2(e) / 2) */
+#define NB_GELU_P 0.2727374808792225f        /* 0.3275911 / sqrt(log2(e)) */
 __device__ __forceinline__ float gelu_erf(float x) {
     const float ax = fabsf(x);
-    const float z = ax * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float y = ax * NB_GELU_K1;
+    const float t = rcp_approx(fmaf(NB_GELU_P, y, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
     p *= t;
-    const float e = fmaf(-p, __expf(-z * z), 1.0f);
-    return fmaf(0.5f * ax, e, 0.5f * x);
+    const float e = fmaf(-p, ex2_approx(-y * y), 1.0f);
+    return 0.5f * fmaf(ax, e, x);
 }
 // gelu(x) and d gelu / dx = Phi(x) + x phi(x) from one erf / one exp evaluation
 __device__ __forceinline__ float gelu_erf_with_grad(float x, float& grad) {
     const float ax = fabsf(x);
-    const float z = ax * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float y = ax * NB_GELU_K1;
+    const float t = rcp_approx(fmaf(NB_GELU_P, y, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
     p *= t;
-    const float ex = __expf(-z * z);          // exp(-x^2 / 2)
+    const float ex = ex2_approx(-y * y);      // exp(-x^2 / 2)
     const float e = fmaf(-p, ex, 1.0f);       // erf(|x| / sqrt 2)
     const float cdf = 0.5f + copysignf(0.5f * e, x);
     grad = fmaf(x * 0.39894228040143267794f, ex, cdf);
-    return fmaf(0.5f * ax, e, 0.5f * x);
+    return 0.5f * fmaf(ax, e, x);
 }
 // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
@@ -119,10 +133,9 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 __device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
-    lo = fminf(fmaxf(lo, -OP_MAX), OP_MAX);
-    hi = fminf(fmaxf(hi, -OP_MAX), OP_MAX);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;  // one F2FP.SATFINITE: round to nearest even, clamp to +-65504 instead of overflowing to inf
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ float2 unpack_op(uint32_t u) {
     __half2 v = *reinterpret_cast<__half2*>(&u);

@@ -153,16 +153,21 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     uint32_t* o = reinterpret_cast<uint32_t*>(out + (long long)row_base * CONV_DIM + c);
     const int valid = m.T0 - t_base;  // rows of this block that are real frames
     if (aux_out == nullptr) {
+        // sliding 10-sample window: frame t+1 reuses samples 5..9 of frame t, so 5 shared loads per frame
+        float xw[10];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xw[5 + j] = xs[j];
 #pragma unroll 4
         for (int t = 0; t < C0_ROWS; ++t) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { xw[j] = xw[5 + j]; xw[5 + j] = xs[5 * t + 5 + j]; }
             uint32_t packed = 0u;
             if (t < valid) {
                 float y0 = w0[10], y1 = w1[10];
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
-                    const float xv = xs[5 * t + j];
-                    y0 = fmaf(w0[j], xv, y0);
-                    y1 = fmaf(w1[j], xv, y1);
+                    y0 = fmaf(w0[j], xw[j], y0);
+                    y1 = fmaf(w1[j], xw[j], y1);
                 }
                 packed = pack_op(gelu_erf(y0), gelu_erf(y1));
             }

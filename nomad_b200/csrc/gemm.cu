@@ -6,6 +6,8 @@
 // x weight^T, which is what nn.Linear / conv-as-GEMM need).
 #include "gemm.cuh"
 
+#include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -22,8 +24,9 @@ struct TileCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages (power of two)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -212,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -256,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ncols = ncols > 32 ? 32 : ncols;
                 if (ccol >= args.umma_n) ncols = 0;
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (uint32_t)(as * BN + ccol) + ((uint32_t)(q * 32) << 16), r);
+                tmem_ld_32x32(tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + ccol) + ((uint32_t)(q * 32) << 16), r);
                 tmem_ld_wait();
                 if (row < args.M && ncols > 0) {
                     float v[32];
@@ -461,6 +464,20 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         return 0;
     }
     if (N > 128) {
+        // 256-wide tiles unless 192-wide ones waste enough fewer CTA-waves to pay for their lower per-tile
+        // efficiency (measured 0.89 on B200, profiles/r01_gemm_probe_v2.log)
+        static const int force_bn = getenv("NOMAD_B200_BN") ? atoi(getenv("NOMAD_B200_BN")) : 0;
+        const double sms = device_sm_count();
+        auto eff = [&](int bn, double tile_eff) {
+            const double tiles = (double)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * batch;
+            const double used = (double)N / (((N + bn - 1) / bn) * (double)bn);
+            return tile_eff * used * tiles / (std::ceil(tiles / sms) * sms);
+        };
+        const bool use192 = force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0);
+        if (use192) {
+            args.umma_n = 192;
+            return launch_tc<192>(st, A, B, args);
+        }
         args.umma_n = 256;
         return launch_tc<256>(st, A, B, args);
     } else if (N > 64) {

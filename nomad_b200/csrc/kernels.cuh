@@ -28,6 +28,10 @@ int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int 
 int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
                      const float* head_b, float* emb, float* pooled_out);
 
+// ---- posconv.cu: grouped positional conv (and its dgrad with flipped, transposed taps) on tcgen05
+int launch_posconv(cudaStream_t st, const op_t* pos_g, long long rows_alloc, long long pos_rows, const op_t* w,
+                   const float* bias, int flags, op_t* out, op_t* aux_out);
+
 // ---- distance.cu
 int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
                       double* row_mean);

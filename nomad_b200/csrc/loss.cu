@@ -656,11 +656,15 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
         pos_bwd_prep_kernel<<<row_blocks, 256, 0, st>>>(L.g_a, ws.x0, ws.pos_y, ws.pos_aux, ws.meta, B, Fe, w.lne_g,
                                                         rows_alloc, L.g_b, L.pos_g);
         NB_LAUNCHED();
-        GemmOperand A{L.pos_g, pos_rows_e, POS_GC, rows_alloc * POS_GC, 0};
-        GemmOperand Bw{w.pos_wt, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
-        GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.pos_dy, nullptr, EMBED);
-        e.out_bstride = POS_GC;
-        NB_TRY(gemm_h16(st, A, Bw, (int)pos_rows_e, POS_GC, POS_K * POS_GC, POS_G, e, impl));
+        if (impl == 0) {
+            NB_TRY(launch_posconv(st, L.pos_g, rows_alloc, pos_rows_e, w.pos_wt, nullptr, 0, L.pos_dy, nullptr));
+        } else {
+            GemmOperand A{L.pos_g, pos_rows_e, POS_GC, rows_alloc * POS_GC, 0};
+            GemmOperand Bw{w.pos_wt, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
+            GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.pos_dy, nullptr, EMBED);
+            e.out_bstride = POS_GC;
+            NB_TRY(gemm_h16(st, A, Bw, (int)pos_rows_e, POS_GC, POS_K * POS_GC, POS_G, e, impl));
+        }
         pos_bwd_finish_kernel<<<row_blocks, 256, 0, st>>>(L.g_b, L.pos_dy, ws.meta, B, Fe, L.g_x0h);
         NB_LAUNCHED();
     }
