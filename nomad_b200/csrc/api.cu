@@ -435,7 +435,12 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_H16, L.b_qkv, nullptr, nullptr, Lb.qkv, 3 * EMBED);
             NB_TRY(gemm_h16(st, A, Bw, (int)F, 3 * EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse));
+        if (impl == 0) {
+            NB_TRY(launch_attention_tc(st, Lb.qkv, ws.meta, p.B, p.max_T, F, Lb.attn, Lb.lse));
+            if (p.max_T > 256) NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 256));
+        } else {
+            NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 0));
+        }
         {
             GemmOperand A{Lb.attn, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_o, EMBED, EMBED, 0, 0};

@@ -215,11 +215,12 @@ __device__ __forceinline__ void load_tile_async(op_t* tile, const op_t* __restri
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__ qkv, const UttMeta* __restrict__ meta,
-                                                        op_t* __restrict__ out, float* __restrict__ lse) {
+                                                        op_t* __restrict__ out, float* __restrict__ lse,
+                                                        int skip_T_le) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
     const int T = meta[b].T;
     const int q0 = qt * ATT_BQ;
-    if (q0 >= T) return;
+    if (q0 >= T || T <= skip_T_le) return;
     const long long f0 = meta[b].frame0;
     __shared__ __align__(128) op_t Qs[ATT_BQ * 64];
     __shared__ __align__(128) op_t Ks[2][ATT_BK * 64];
@@ -342,9 +343,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const op_t* __restrict__
     }
 }
 
-int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse) {
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse,
+                     int skip_T_le) {
     dim3 grid((max_T + ATT_BQ - 1) / ATT_BQ, HEADS, B);
-    attention_kernel<<<grid, 128, 0, st>>>(qkv, meta, out, lse);
+    attention_kernel<<<grid, 128, 0, st>>>(qkv, meta, out, lse, skip_T_le);
     NB_LAUNCHED();
     return 0;
 }

@@ -282,6 +282,164 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster share one 256 x 256 output tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile (128 rows); the pair's tensor cores read both halves,
+// so per SM the TMA traffic into shared memory drops from 48 to 32 KB per K-block and the B operand is read
+// once per pair.  The single-CTA kernel is shared-memory-port bound at ~2/3 of the tensor peak (96 B/clk of
+// operand reads + 96 B/clk of TMA writes against a 128 B/clk port); the pair halves the B share of both.
+// The even CTA (leader) issues every MMA and owns the full / tmem_empty barriers; commits are multicast.
+struct Pair256 {
+    static constexpr int BN = 256;
+    static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of B
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+    using Cfg = Pair256;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_tiles = args.m_tiles * args.n_tiles * args.batch;  // m_tiles counts 256-row tiles here
+    const int k_blocks = (args.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);  // epilogue warps of BOTH CTAs arrive on the leader's
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_slot, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                const int n_blk = tile % args.n_tiles;
+                const int m_blk = (tile / args.n_tiles) % args.m_tiles;
+                const int b = tile / (args.n_tiles * args.m_tiles);
+                const int row0 = m_blk * 256 + (int)rank * BM;
+                const int col0 = n_blk * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    if (args.a_wrap > 0) {
+                        const int kk = kb * BK;
+                        tma_load_3d_pair(sa, &tmA, &full_bar[stage], kk % args.a_wrap, row0 + kk / args.a_wrap, b);
+                    } else {
+                        tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * BK, row0, b);
+                    }
+                    tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * BK, col0, b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_h16(256, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int h = ew >> 2;
+        constexpr int HALF = BN / 2;
+        int it = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+            const int n_blk = tile % args.n_tiles;
+            const int m_blk = (tile / args.n_tiles) % args.m_tiles;
+            const int b = tile / (args.n_tiles * args.m_tiles);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < HALF / 32; ++c) {
+                const int ccol = h * HALF + c * 32;
+                const int col0 = n_blk * BN + ccol;
+                int ncols = args.N - col0;
+                ncols = ncols > 32 ? 32 : ncols;
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (uint32_t)(as * 256 + ccol) + ((uint32_t)(q * 32) << 16), r);
+                tmem_ld_wait();
+                if (row < args.M && ncols > 0) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    epilogue_chunk(args.epi, v, row, col0, ncols, b);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SIMT check kernel: same operands, same epilogue, one thread per output element.  Used by the GPU
 // parity tests to cross-check the tensor-core kernel on device (and selectable with
 // NOMAD_B200_GEMM=simt for debugging); never the default.
@@ -440,6 +598,29 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     return 0;
 }
 
+static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    using Cfg = Pair256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
+    NB_TRY(make_operand_map(&tmB, B, args.K, args.batch, Cfg::BN / 2));
+    args.umma_n = Cfg::BN;
+    args.m_tiles = (args.M + 255) / 256;
+    args.n_tiles = (args.N + Cfg::BN - 1) / Cfg::BN;
+    const long long tiles = (long long)args.m_tiles * args.n_tiles * args.batch;
+    int pairs = device_sm_count() / 2;
+    if (tiles < pairs) pairs = (int)tiles;
+    NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
+    gemm_tc_pair_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
+    NB_LAUNCHED();
+    NB_TRY(prof_end(st));
+    return 0;
+}
+
 int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
@@ -463,6 +644,10 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         NB_LAUNCHED();
         return 0;
     }
+    // CTA pairs (cta_group::2) for the big GEMMs; NOMAD_B200_PAIR=0 falls back to the single-CTA kernel
+    static const int use_pair = getenv("NOMAD_B200_PAIR") ? atoi(getenv("NOMAD_B200_PAIR")) : 1;
+    if (use_pair && N >= 256 && (long long)((M + 255) / 256) * ((N + 255) / 256) * batch >= device_sm_count() / 2)
+        return launch_pair(st, A, B, args);
     if (N > 128) {
         // 256-wide tiles unless 192-wide ones waste enough fewer CTA-waves to pay for their lower per-tile
         // efficiency (measured 0.89 on B200, profiles/r01_gemm_probe_v2.log)

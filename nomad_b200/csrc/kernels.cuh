@@ -24,7 +24,12 @@ int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, co
 // layer_out[(utt * T + t) * 768 + c] for a uniform batch
 int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
                  const float* b, float* x, op_t* xh, float* layer_out, int layer_T);
-int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse);
+// streaming mma.sync kernel (any T); utterances with T <= skip_T_le are left to the tcgen05 kernel
+int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse,
+                     int skip_T_le);
+// attention_tc.cu: tcgen05 kernel for utterances with T <= 256 (skips longer ones)
+int launch_attention_tc(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, long long frames,
+                        op_t* out, float* lse);
 int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
                      const float* head_b, float* emb, float* pooled_out);
 

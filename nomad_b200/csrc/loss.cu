@@ -7,6 +7,7 @@
 // kernel divides it out.  fairseq's GradMultiply(feature_grad_mult) on the conv features is applied at
 // the LayerNorm(512) boundary.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/nomad_b200.h"
@@ -39,10 +40,12 @@ __device__ __forceinline__ float normalise768(Row768f& r) {
     const float mean = warp_sum(s) * (1.0f / EMBED);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) { r.v[i] -= mean; q = fmaf(r.v[i], r.v[i], q); }
+    for (int i = 0; i < 24; ++i) { r.v[i] = __fsub_rn(r.v[i], mean); q = fmaf(r.v[i], r.v[i], q); }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / EMBED) + 1e-5f);
+    // explicit rounding: the compiler must not contract this product into a later (est - clean) subtraction,
+    // or identical inputs stop giving an exactly zero L1 term / zero gradient sign
 #pragma unroll
-    for (int i = 0; i < 24; ++i) r.v[i] *= rstd;
+    for (int i = 0; i < 24; ++i) r.v[i] = __fmul_rn(r.v[i], rstd);
     return rstd;
 }
 __device__ __forceinline__ void store_row768(const Row768f& r, float* __restrict__ x, op_t* __restrict__ xh, int lane) {
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256) l1_layer_kernel(const float* __restrict__
             normalise768(e);
             normalise768(c);
 #pragma unroll
-            for (int i = 0; i < 24; ++i) tot += fabsf((e.v[i] - c.v[i]) * gg.v[i]);  // beta cancels
+            for (int i = 0; i < 24; ++i) tot += fabsf(__fsub_rn(e.v[i], c.v[i]) * gg.v[i]);  // beta cancels
         }
     }
     tot = warp_sum(tot);
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) ln768_bwd_kernel(const float* __restrict_
         normalise768(xc);
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
-            const float d = (xh.v[i] - xc.v[i]) * gg.v[i];  // x_est - x_clean (beta cancels)
+            const float d = __fsub_rn(xh.v[i], xc.v[i]) * gg.v[i];  // x_est - x_clean (beta cancels)
             g.v[i] += d > 0.f ? seed : (d < 0.f ? -seed : 0.f);
         }
     }
@@ -602,6 +605,12 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
     NB_LAUNCHED();
     loss_finalize_kernel<<<1, 1, 0, st>>>(L.acc, 1.0 / numel, 1.0 / ((double)B * EMB), loss_dev);
     NB_LAUNCHED();
+    if (getenv("NOMAD_B200_DEBUG_LOSS")) {  // per-term L1 sums, for debugging only (synchronises)
+        double hacc[16];
+        NB_CUDA(cudaStreamSynchronize(st));
+        NB_CUDA(cudaMemcpy(hacc, L.acc, sizeof(hacc), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 13; ++i) fprintf(stderr, "[nomad_b200] L1 term %2d: sum |diff| = %.9g\n", i, hacc[i]);
+    }
     if (!with_grad) return 0;
 
     // ------------------------------------------------------------------ backward (estimate half)

@@ -59,6 +59,19 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
     return d;  // layout type 0 = SWIZZLE_NONE
 }
 
+// tcgen05.mma with both descriptors passed as 32-bit halves (no 64-bit arithmetic at the call site)
+__device__ __forceinline__ void umma_f16_parts(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(PC_THREADS, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmW, const PosConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -135,25 +148,37 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant
                 mbar_wait(&tmem_empty[sb], sphase ^ 1);
                 mbar_wait(&slab_full[sb], sphase);
                 tc_fence_after();
-                const uint32_t slab_addr = smem_u32(slab[sb]);
+                // Descriptors as (lo, hi) 32-bit halves: the start-address field sits in the low word and never
+                // carries, so advancing to another tap / sub-tile / K-chunk is ONE 32-bit add per MMA.  The single
+                // issuing thread has to sustain one N=48 MMA every ~30 cycles, so its instruction count matters.
+                const uint64_t da0 = umma_desc_noswz(smem_u32(slab[sb]), PC_LBO, 128);
+                const uint32_t da_lo = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32);
                 const uint32_t d_base = tmem_base + sb * (PC_SUB * PC_ACC_STRIDE);
-                for (int kb = 0; kb < PC_KBLOCKS; ++kb) {
-                    mbar_wait(&b_full[stage], phase);
-                    tc_fence_after();
-                    const uint64_t db = umma_desc_sw128(smem_u32(bst + stage * PC_BSTAGE_BYTES));
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int kb3 = 0; kb3 < PC_KBLOCKS / 3; ++kb3) {
+                    // 3 weight blocks = 12 K-steps of 16 = 4 taps x 3 channel thirds; everything below is unrolled
+                    const uint32_t a_tap0 = da_lo + 4 * kb3;  // tap * 16 B >> 4
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const int s = kb * 4 + k4;        // K step of 16: tap = s / 3, 16-channel third = s % 3
-                        const int tap = s / 3, cc = s - 3 * tap;
-                        const uint32_t a0 = slab_addr + (2 * cc) * PC_LBO + tap * 16;
+                    for (int j = 0; j < 3; ++j) {
+                        mbar_wait(&b_full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t db0 = umma_desc_sw128(smem_u32(bst + stage * PC_BSTAGE_BYTES));
+                        const uint32_t db_lo = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
 #pragma unroll
-                        for (int sub = 0; sub < PC_SUB; ++sub) {
-                            const uint64_t da = umma_desc_noswz(a0 + sub * 128 * 16, PC_LBO, 128);
-                            umma_f16(d_base + sub * PC_ACC_STRIDE, da, db + (uint64_t)(2 * k4), idesc, s ? 1u : 0u);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const int t = 4 * j + k4;              // 0..11 (compile time)
+                            const int tap = t / 3, cc = t % 3;
+                            const uint32_t a_lo = a_tap0 + tap + (2 * cc) * (PC_LBO >> 4);
+#pragma unroll
+                            for (int sub = 0; sub < PC_SUB; ++sub)
+                                umma_f16_parts(d_base + sub * PC_ACC_STRIDE, a_lo + sub * 128, da_hi, db_lo + 2 * k4, db_hi,
+                                               idesc, acc);
+                            acc = 1;
                         }
+                        umma_commit(&b_empty[stage]);
+                        if (++stage == PC_BSTAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&b_empty[stage]);
-                    if (++stage == PC_BSTAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&slab_empty[sb]);
                 umma_commit(&tmem_full[sb]);
