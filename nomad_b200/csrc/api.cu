@@ -88,6 +88,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
         }
         w.ln0_out = (op_t*)take(2ull * CONV_DIM * (F + 8));
     }
+    w.ln_stats = (float*)take(4ull * 2 * 2 * F);  // two alternating slots
     w.x = (float*)take(4ull * EMBED * F);
     w.xh = (op_t*)take(2ull * EMBED * F);
     w.pos_g = (op_t*)take(2ull * POS_G * POS_GC * (p.pos_rows + POS_K));
@@ -441,13 +442,26 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
         } else {
             NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 0));
         }
+        // Residual stream bookkeeping: a LayerNorm kernel emits only the 16-bit operand + (mean, rstd) per row;
+        // the next residual-adding GEMM epilogue rebuilds LN(pre) from the pre-LN buffer (EPI_RESID_LN).  Only the
+        // encoder-LN output (layer 0 input) and the last layer's output exist as fp32 tensors.
+        float* st1 = ws.ln_stats;            // stats of this layer's self_attn_layer_norm input
+        float* st2 = ws.ln_stats + 2 * F;    // stats of a layer's final_layer_norm input
         {
             GemmOperand A{Lb.attn, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_o, EMBED, EMBED, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_o, ws.x, Lb.pre1, nullptr, EMBED);
+            GemmEpilogue e;
+            if (l == 0) {
+                e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_o, ws.x, Lb.pre1, nullptr, EMBED);
+            } else {
+                e = epi_linear(EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32, L.b_o, ws.layer[l - 1].pre2, Lb.pre1, nullptr, EMBED);
+                e.ln_stats = st2;
+                e.ln_g = w.layer[l - 1].ln2_g;
+                e.ln_b = w.layer[l - 1].ln2_b;
+            }
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, p.B, F, L.ln1_g, L.ln1_b, ws.x, ws.xh, nullptr, 0));
+        NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, p.B, F, L.ln1_g, L.ln1_b, nullptr, ws.xh, st1, nullptr, 0));
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
             GemmOperand Bw{L.w_fc1, FFN, EMBED, 0, 0};
@@ -461,11 +475,15 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
         {
             GemmOperand A{ws.ffn_h, F, FFN, 0, 0};
             GemmOperand Bw{L.w_fc2, EMBED, FFN, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID | EPI_OUT_F32, L.b_fc2, ws.x, Lb.pre2, nullptr, EMBED);
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32, L.b_fc2, Lb.pre1, Lb.pre2, nullptr, EMBED);
+            e.ln_stats = st1;
+            e.ln_g = L.ln1_g;
+            e.ln_b = L.ln1_b;
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, FFN, 1, e, impl));
         }
         float* lo = layers_out ? layers_out + (size_t)l * p.B * layer_T * EMBED : nullptr;
-        NB_TRY(launch_ln768(st, Lb.pre2, ws.meta, p.B, F, L.ln2_g, L.ln2_b, ws.x, ws.xh, lo, layer_T));
+        const bool last = l == LAYERS - 1;
+        NB_TRY(launch_ln768(st, Lb.pre2, ws.meta, p.B, F, L.ln2_g, L.ln2_b, last ? ws.x : nullptr, ws.xh, st2, lo, layer_T));
     }
     return 0;
 }

@@ -40,8 +40,8 @@ struct Row768 {
     float v[24];
 };
 
-__device__ __forceinline__ void ln768_normalise(Row768& r, const float* __restrict__ g, const float* __restrict__ bta,
-                                                int lane) {
+__device__ __forceinline__ float2 ln768_normalise(Row768& r, const float* __restrict__ g, const float* __restrict__ bta,
+                                                  int lane) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 24; ++i) s += r.v[i];
@@ -61,6 +61,7 @@ __device__ __forceinline__ void ln768_normalise(Row768& r, const float* __restri
         v[4] = (v[4] - mean) * rstd * g1.x + b1.x; v[5] = (v[5] - mean) * rstd * g1.y + b1.y;
         v[6] = (v[6] - mean) * rstd * g1.z + b1.z; v[7] = (v[7] - mean) * rstd * g1.w + b1.w;
     }
+    return make_float2(mean, rstd);
 }
 
 __device__ __forceinline__ void row768_store(const Row768& r, long long f, int lane, float* __restrict__ x,
@@ -69,9 +70,11 @@ __device__ __forceinline__ void row768_store(const Row768& r, long long f, int l
     for (int h = 0; h < 3; ++h) {
         const int c0 = (lane + 32 * h) * 8;
         const float* v = r.v + 8 * h;
-        float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
-        xo[0] = make_float4(v[0], v[1], v[2], v[3]);
-        xo[1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (x != nullptr) {
+            float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
+            xo[0] = make_float4(v[0], v[1], v[2], v[3]);
+            xo[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
         *reinterpret_cast<uint4*>(xh + f * EMBED + c0) =
             make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
     }
@@ -81,9 +84,11 @@ __device__ __forceinline__ void row768_store_zero(long long f, int lane, float* 
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
         const int c0 = (lane + 32 * h) * 8;
-        float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
-        xo[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xo[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x != nullptr) {
+            float4* xo = reinterpret_cast<float4*>(x + f * EMBED + c0);
+            xo[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            xo[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         *reinterpret_cast<uint4*>(xh + f * EMBED + c0) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
@@ -129,7 +134,8 @@ int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, co
 __global__ void __launch_bounds__(256) ln768_kernel(const float* __restrict__ pre, const UttMeta* __restrict__ meta,
                                                     int B, long long frames, const float* __restrict__ g,
                                                     const float* __restrict__ bta, float* __restrict__ x,
-                                                    op_t* __restrict__ xh, float* __restrict__ layer_out, int layer_T) {
+                                                    op_t* __restrict__ xh, float* __restrict__ stats,
+                                                    float* __restrict__ layer_out, int layer_T) {
     const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (f >= frames) return;
     const int lane = threadIdx.x & 31;
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(256) ln768_kernel(const float* __restrict__ pr
     const int t = (int)f - meta[b].frame0;
     if (t >= meta[b].T) {
         row768_store_zero(f, lane, x, xh);
+        if (stats != nullptr && lane == 0) reinterpret_cast<float2*>(stats)[f] = make_float2(0.f, 0.f);
         return;
     }
     Row768 r;
@@ -148,8 +155,9 @@ __global__ void __launch_bounds__(256) ln768_kernel(const float* __restrict__ pr
         float* v = r.v + 8 * h;
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
     }
-    ln768_normalise(r, g, bta, lane);
+    const float2 st = ln768_normalise(r, g, bta, lane);
     row768_store(r, f, lane, x, xh);
+    if (stats != nullptr && lane == 0) reinterpret_cast<float2*>(stats)[f] = st;
     if (layer_out != nullptr) {
         float* lo = layer_out + ((long long)b * layer_T + t) * EMBED;
 #pragma unroll
@@ -164,8 +172,9 @@ __global__ void __launch_bounds__(256) ln768_kernel(const float* __restrict__ pr
 }
 
 int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
-                 const float* b, float* x, op_t* xh, float* layer_out, int layer_T) {
-    ln768_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(pre, meta, B, frames, g, b, x, xh, layer_out, layer_T);
+                 const float* b, float* x, op_t* xh, float* stats, float* layer_out, int layer_T) {
+    ln768_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(pre, meta, B, frames, g, b, x, xh, stats, layer_out,
+                                                              layer_T);
     NB_LAUNCHED();
     return 0;
 }

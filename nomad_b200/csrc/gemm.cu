@@ -93,6 +93,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
+    if (flags & EPI_RESID_LN) {
+        // residual = LayerNorm(pre-LN row) rebuilt from its saved statistics: saves the fp32 write + read of the
+        // normalised residual stream (the LayerNorm kernel then only emits the 16-bit GEMM operand)
+        const float4* rp = reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0);
+        const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row);
+        const float4* gp = reinterpret_cast<const float4*>(e.ln_g + col0);
+        const float4* bp = reinterpret_cast<const float4*>(e.ln_b + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j * 4 < ncols) {
+                const float4 t = __ldg(rp + j), g = __ldg(gp + j), bb = __ldg(bp + j);
+                v[4 * j + 0] += fmaf((t.x - st.x) * st.y, g.x, bb.x);
+                v[4 * j + 1] += fmaf((t.y - st.x) * st.y, g.y, bb.y);
+                v[4 * j + 2] += fmaf((t.z - st.x) * st.y, g.z, bb.z);
+                v[4 * j + 3] += fmaf((t.w - st.x) * st.y, g.w, bb.w);
+            }
+        }
+    }
     if (flags & EPI_OUT_F32) {
         float4* op = reinterpret_cast<float4*>(e.out_f + off);
 #pragma unroll
@@ -130,8 +148,46 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, 
     }
     if (flags & EPI_MUL_AUX) v *= op2f(e.aux[off]);
     if (flags & EPI_RESID) v += e.resid[row * e.ldr + col + (long long)b * e.resid_bstride];
+    if (flags & EPI_RESID_LN) {
+        const float mean = e.ln_stats[2 * row], rstd = e.ln_stats[2 * row + 1];
+        v += fmaf((e.resid[row * e.ldr + col] - mean) * rstd, e.ln_g[col], e.ln_b[col]);
+    }
     if (flags & EPI_OUT_F32) e.out_f[off] = v;
     if (flags & EPI_OUT_H16) e.out_h[off] = f2op(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The TMEM load of chunk c+1 is in flight
+// while chunk c is processed, and the accumulator stage is handed back to the MMA warp as soon as the last load
+// has landed (before that chunk's math and stores).
+template <int CHUNKS, bool PAIR>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
+                                              int ccol_first, int b, uint64_t* tmem_empty_bar, int lane) {
+    uint32_t r[2][32];
+    tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < CHUNKS) {
+            tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+            }
+        }
+        const int col0 = col_first + c * 32;
+        int ncols = args.N - col0;
+        ncols = ncols > 32 ? 32 : ncols;
+        if (ccol_first + c * 32 >= args.umma_n) ncols = 0;
+        if (row < args.M && ncols > 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
+            epilogue_chunk(args.epi, v, row, col0, ncols, b);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,26 +307,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * BM + q * 32 + lane;
-#pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
-                const int ccol = h * HALF + c * 32;  // column inside the tile
-                const int col0 = n_blk * BN + ccol;
-                int ncols = args.N - col0;
-                ncols = ncols > 32 ? 32 : ncols;
-                if (ccol >= args.umma_n) ncols = 0;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + ccol) + ((uint32_t)(q * 32) << 16), r);
-                tmem_ld_wait();
-                if (row < args.M && ncols > 0) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epilogue_chunk(args.epi, v, row, col0, ncols, b);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            epilogue_tile<CHUNKS, false>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
+                                         row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane);
         }
     }
     tc_fence_before();
@@ -410,25 +448,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
-#pragma unroll 1
-            for (int c = 0; c < HALF / 32; ++c) {
-                const int ccol = h * HALF + c * 32;
-                const int col0 = n_blk * BN + ccol;
-                int ncols = args.N - col0;
-                ncols = ncols > 32 ? 32 : ncols;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (uint32_t)(as * 256 + ccol) + ((uint32_t)(q * 32) << 16), r);
-                tmem_ld_wait();
-                if (row < args.M && ncols > 0) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epilogue_chunk(args.epi, v, row, col0, ncols, b);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
+            epilogue_tile<HALF / 32, true>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane);
         }
     }
     tc_fence_before();

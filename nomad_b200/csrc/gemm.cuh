@@ -14,6 +14,7 @@ enum : int {
     EPI_OUT_H16 = 16, // store op_t
     EPI_MUL_AUX = 32,  // * aux[row, col] (op_t)  -- dgrad through GELU: aux holds gelu'(pre-activation)
     EPI_CDIST = 64,
+    EPI_RESID_LN = 256,  // + LayerNorm(resid row) recomputed from saved (mean, rstd): (r - mean) * rstd * g + b
     EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
 };
 
@@ -39,6 +40,9 @@ struct GemmEpilogue {
     const float* resid;       // fp32, element (row, col) at resid[row * ldr + col + b * resid_bstride]
     long long ldr;
     long long resid_bstride;
+    const float* ln_stats;    // EPI_RESID_LN: [rows][2] = mean, rstd of the resid row
+    const float* ln_g;        // [N]
+    const float* ln_b;        // [N]
     const op_t* aux;          // 16-bit, same indexing as out (ldo / out_bstride)
     op_t* aux_out;            // EPI_SAVE_DGELU target, same indexing as out
     float* out_f;             // element (row, col) of batch b at out[row * ldo + col + b * out_bstride]

@@ -20,10 +20,10 @@ int launch_pos_scatter(cudaStream_t st, const float* x, const UttMeta* meta, int
 // x = LN(x0 + y[pos row]) on valid frames, 0 elsewhere
 int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, const UttMeta* meta, int B,
                          long long frames, const float* g, const float* b, float* x, op_t* xh);
-// x = LN(pre) on valid frames, 0 elsewhere; optional compact copy of the result (loss path):
-// layer_out[(utt * T + t) * 768 + c] for a uniform batch
+// LN(pre) on valid frames, 0 elsewhere -> 16-bit xh; optional fp32 x, optional (mean, rstd) per row (so a later
+// GEMM epilogue can rebuild the fp32 residual), optional compact copy layer_out[(utt * T + t) * 768 + c]
 int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
-                 const float* b, float* x, op_t* xh, float* layer_out, int layer_T);
+                 const float* b, float* x, op_t* xh, float* stats, float* layer_out, int layer_T);
 // streaming mma.sync kernel (any T); utterances with T <= skip_T_le are left to the tcgen05 kernel
 int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse,
                      int skip_T_le);

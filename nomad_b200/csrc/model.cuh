@@ -103,6 +103,7 @@ struct Workspace {
     op_t* pos_g;         // [16][pos_rows + 128][48]
     op_t* pos_y;         // [pos_rows][768] GELU(pos conv)
     op_t* pos_aux;       // save mode: gelu' of the pos conv pre-activation, [pos_rows][768]
+    float* ln_stats;     // frames x 2: (mean, rstd) of the most recent LayerNorm(768) input rows
     float* x;            // residual stream, frames x 768 fp32
     op_t* xh;            // 16-bit copy (GEMM operand)
     op_t* ffn_h;         // frames x 3072
