@@ -667,18 +667,24 @@ int nomad_b200_layers_fwd(nomad_b200_handle* hh, const float* wav_dev, int B, in
     return 0;
 }
 
+// Small problems (and the SIMT cross-check) use the fp32 direct-difference kernel; everything else the
+// tensor-core Gram kernel.
+static bool cdist_use_tc(int64_t n, int64_t m, int gemm_impl) { return gemm_impl == 0 && n * m >= (1 << 16); }
+
 size_t nomad_b200_cdist_workspace_bytes(int64_t n, int64_t m) {
-    (void)n; (void)m;
-    return 1024;
+    if (n < 0 || m < 0) return 0;
+    return cdist_use_tc(n, m, 0) ? cdist_tc_workspace(n, m) : 1024;
 }
 
 int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev, int64_t m, float* dm_dev,
                           double* row_mean_dev, void* workspace_dev, size_t workspace_bytes, int gemm_impl,
                           void* stream) {
-    (void)workspace_dev; (void)workspace_bytes; (void)gemm_impl;
     NB_CHECK(n >= 0 && m >= 0, "cdist: negative size");
     NB_CHECK(n == 0 || (deg_dev && row_mean_dev), "cdist: null pointer");
     NB_CHECK(m == 0 || nmr_dev, "cdist: null pointer");
+    if (cdist_use_tc(n, m, gemm_impl))
+        return launch_cdist_tc((cudaStream_t)stream, deg_dev, n, nmr_dev, m, dm_dev, row_mean_dev, workspace_dev,
+                               workspace_bytes, 0);
     return launch_cdist_fp32((cudaStream_t)stream, deg_dev, n, nmr_dev, m, dm_dev, row_mean_dev);
 }
 
@@ -687,8 +693,9 @@ int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nm
     NB_CHECK(n > 0 && m > 0 && deg_host && nmr_host && row_mean_host, "cdist_host: bad arguments");
     const size_t a_b = align_up((size_t)n * EMB * 4, 1024), b_b = align_up((size_t)m * EMB * 4, 1024);
     const size_t dm_b = dm_host ? align_up((size_t)n * m * 4, 1024) : 0, rm_b = align_up((size_t)n * 8, 1024);
-    NB_CHECK(workspace_dev && workspace_bytes >= a_b + b_b + dm_b + rm_b,
-             "cdist_host: workspace too small (%zu < %zu bytes)", workspace_bytes, a_b + b_b + dm_b + rm_b);
+    const size_t core = align_up(nomad_b200_cdist_workspace_bytes(n, m), 1024);
+    NB_CHECK(workspace_dev && workspace_bytes >= a_b + b_b + dm_b + rm_b + core,
+             "cdist_host: workspace too small (%zu < %zu bytes)", workspace_bytes, a_b + b_b + dm_b + rm_b + core);
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)workspace_dev;
     float* a_d = (float*)base;
@@ -697,7 +704,7 @@ int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nm
     double* rm_d = (double*)(base + a_b + b_b + dm_b);
     NB_CUDA(cudaMemcpyAsync(a_d, deg_host, (size_t)n * EMB * 4, cudaMemcpyHostToDevice, st));
     NB_CUDA(cudaMemcpyAsync(b_d, nmr_host, (size_t)m * EMB * 4, cudaMemcpyHostToDevice, st));
-    NB_TRY(launch_cdist_fp32(st, a_d, n, b_d, m, dm_d, rm_d));
+    NB_TRY(nomad_b200_cdist_mean(a_d, n, b_d, m, dm_d, rm_d, base + a_b + b_b + dm_b + rm_b, core, 0, stream));
     if (dm_host) NB_CUDA(cudaMemcpyAsync(dm_host, dm_d, (size_t)n * m * 4, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaMemcpyAsync(row_mean_host, rm_d, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));

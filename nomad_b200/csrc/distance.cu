@@ -5,6 +5,8 @@
 // (unit-norm embeddings give distances down to ~0.1 where the Gram form ||a||^2 + ||b||^2 - 2ab loses
 // 3-4 digits), so it meets the 1e-5 bound against scipy's float64 result without tricks.  Row sums are
 // accumulated in fp64.
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace nb {
@@ -79,9 +81,89 @@ __global__ void __launch_bounds__(256) cdist_fp32_kernel(const float* __restrict
     }
 }
 
+
 __global__ void scale_rows_kernel(double* v, long long n, double s) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] *= s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core path: Gram matrix on tcgen05 from split-fp16 operands.
+//   x = hi + lo (hi = fp16(S x), lo = fp16(S x - hi), S = 64 keeps lo out of the fp16 subnormals)
+//   <a, b> ~ (a_hi.b_hi + a_lo.b_hi + a_hi.b_lo) / S^2   -- one K = 768 GEMM over [hi | lo | hi] x [hi | hi | lo]
+// which carries ~21 significant bits, enough for the 1e-5 bound once near-zero distances are re-evaluated
+// exactly in the epilogue (gemm.cu: cdist_chunk).  Norms are fp32 from the original rows.
+static constexpr float CD_SCALE = 64.0f;
+
+__global__ void __launch_bounds__(256) cdist_prep_kernel(const float* __restrict__ x, long long n, int is_b,
+                                                         op_t* __restrict__ split, float* __restrict__ norm) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float4* p = reinterpret_cast<const float4*>(x + row * CD_DIM);
+    const float4 a = __ldg(p + 2 * lane), b = __ldg(p + 2 * lane + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float s = 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x0 = v[2 * i] * CD_SCALE, x1 = v[2 * i + 1] * CD_SCALE;
+        s = fmaf(v[2 * i], v[2 * i], s);
+        s = fmaf(v[2 * i + 1], v[2 * i + 1], s);
+        hi[i] = pack_op(x0, x1);
+        const float2 h = unpack_op(hi[i]);
+        lo[i] = pack_op(x0 - h.x, x1 - h.y);
+    }
+    s = warp_sum(s);
+    if (lane == 0) norm[row] = s;
+    uint4* o = reinterpret_cast<uint4*>(split + row * (3 * CD_DIM));
+    const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    // A rows: [hi | lo | hi]   B rows: [hi | hi | lo]
+    o[lane] = H;
+    o[32 + lane] = is_b ? H : L;
+    o[64 + lane] = is_b ? L : H;
+}
+
+size_t cdist_tc_workspace(long long n, long long m) {
+    auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+    return al((size_t)n * 3 * CD_DIM * 2) + al((size_t)m * 3 * CD_DIM * 2) + al((size_t)n * 4) + al((size_t)m * 4) + 1024;
+}
+
+int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
+                    double* row_mean, void* ws, size_t ws_bytes, int impl) {
+    if (n <= 0) return 0;
+    NB_CUDA(cudaMemsetAsync(row_mean, 0, sizeof(double) * n, st));
+    if (m <= 0) return 0;
+    NB_CHECK(ws != nullptr && ws_bytes >= cdist_tc_workspace(n, m), "cdist: workspace too small (%zu < %zu bytes)", ws_bytes,
+             cdist_tc_workspace(n, m));
+    NB_CHECK(n < (1LL << 31) && m < (1LL << 31), "cdist: too many rows for one call; chunk it");
+    auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+    char* base = (char*)ws;
+    op_t* sa = (op_t*)base;
+    op_t* sb = (op_t*)(base + al((size_t)n * 3 * CD_DIM * 2));
+    float* na = (float*)((char*)sb + al((size_t)m * 3 * CD_DIM * 2));
+    float* nbv = (float*)((char*)na + al((size_t)n * 4));
+    cdist_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, n, 0, sa, na);
+    NB_LAUNCHED();
+    cdist_prep_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(b, m, 1, sb, nbv);
+    NB_LAUNCHED();
+    GemmOperand A{sa, n, 3 * CD_DIM, 0, 0};
+    GemmOperand Bw{sb, m, 3 * CD_DIM, 0, 0};
+    GemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.flags = EPI_CDIST;
+    e.out_f = dm;
+    e.ldo = m;
+    e.norm_a = na;
+    e.norm_b = nbv;
+    e.row_sum = row_mean;
+    e.cd_a = a;
+    e.cd_b = b;
+    e.cd_inv_scale = 1.0f / (CD_SCALE * CD_SCALE);
+    NB_TRY(gemm_h16(st, A, Bw, (int)n, (int)m, 3 * CD_DIM, 1, e, impl));
+    scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_mean, n, 1.0 / (double)m);
+    NB_LAUNCHED();
+    return 0;
 }
 
 int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,

@@ -18,16 +18,18 @@ static constexpr int BK = 64;  // 64 op_t = 128 B = one swizzle-128B row
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+static constexpr float CD_REFINE = 1e-3f;  // squared distances below this are re-evaluated exactly (see cdist_chunk)
 
 template <int BN>
 struct TileCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 5 : 7));
     static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages (power of two)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;  // coalescing buffers of the epilogue warps
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -39,11 +41,63 @@ struct GemmArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue for one (row, 32-column chunk): v[] holds the fp32 accumulators.
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, int col0,
-                                               int ncols, int b) {
+// Staged, coalesced global stores.  TMEM hands every lane one ROW of the tile, so a direct store instruction
+// would touch 32 different rows with 16 B each: half-sector writes that L2 has to read-modify-write (measured:
+// the N=768, K=768 out-projection ran at 370 TFLOP/s because of it).  Instead each epilogue warp owns a 4 KB
+// shared-memory staging buffer (32 rows x 128 B, 16-byte pieces XOR-swizzled): lanes deposit their row, then
+// the warp reads it back transposed so that consecutive lanes store consecutive 16 B of the SAME row --
+// full 32 B sectors / 128 B lines per instruction.
+static constexpr int STAGE_BYTES_PER_WARP = 4096;
+
+__device__ __forceinline__ void stage_put_f32(float* stage, const float (&v)[32], int lane) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        *reinterpret_cast<float4*>(stage + lane * 32 + ((p ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+}
+// out points at (first row of this warp, first column of the chunk)
+__device__ __forceinline__ void stage_flush_f32(const float* stage, float* out, long long ld, int rows_valid, int ncols,
+                                                int lane) {
+    __syncwarp();
+    const int p = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rl = k * 4 + (lane >> 3);
+        if (rl < rows_valid && p * 4 < ncols)
+            *reinterpret_cast<float4*>(out + rl * ld + p * 4) =
+                *reinterpret_cast<const float4*>(stage + rl * 32 + ((p ^ (rl & 7)) << 2));
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void stage_put_h16(op_t* stage, const float (&v)[32], int lane) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<uint4*>(stage + lane * 32 + ((p ^ ((lane >> 1) & 3)) << 3)) =
+            make_uint4(pack_op(v[8 * p], v[8 * p + 1]), pack_op(v[8 * p + 2], v[8 * p + 3]),
+                       pack_op(v[8 * p + 4], v[8 * p + 5]), pack_op(v[8 * p + 6], v[8 * p + 7]));
+}
+__device__ __forceinline__ void stage_flush_h16(const op_t* stage, op_t* out, long long ld, int rows_valid, int ncols,
+                                                int lane) {
+    __syncwarp();
+    const int p = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rl = k * 8 + (lane >> 2);
+        if (rl < rows_valid && p * 8 < ncols)
+            *reinterpret_cast<uint4*>(out + rl * ld + p * 8) =
+                *reinterpret_cast<const uint4*>(stage + rl * 32 + ((p ^ ((rl >> 1) & 3)) << 3));
+    }
+    __syncwarp();
+}
+
+// Epilogue for one warp x 32-column chunk: lane owns row `row` (v[] = its fp32 accumulators).  Executed by all
+// 32 lanes (staging is warp-collective); lanes whose row is past M skip the loads and are never flushed.
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
+                                               int rows_valid, int col0, int ncols, int b, float* stage, int lane) {
     const int flags = e.flags;
-    if (flags & EPI_BIAS) {
+    const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
+    const long long woff = (row - lane) * e.ldo + col0 + (long long)b * e.out_bstride;  // this warp's first row
+    if (row_ok && (flags & EPI_BIAS)) {
         const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bstride + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -53,22 +107,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     if (flags & EPI_SAVE_DGELU) {
-        uint4* gp = reinterpret_cast<uint4*>(e.aux_out + off);
+        float g[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float g[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * j + i] = gelu_erf_with_grad(v[8 * j + i], g[i]);
-            if (j * 8 < ncols)
-                gp[j] = make_uint4(pack_op(g[0], g[1]), pack_op(g[2], g[3]), pack_op(g[4], g[5]), pack_op(g[6], g[7]));
-        }
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_with_grad(v[j], g[j]);
+        stage_put_h16(reinterpret_cast<op_t*>(stage), g, lane);
+        stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
     } else if (flags & EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
-    if (flags & EPI_MUL_AUX) {
+    if (row_ok && (flags & EPI_MUL_AUX)) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -82,7 +131,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    if (flags & EPI_RESID) {
+    if (row_ok && (flags & EPI_RESID)) {
         const float4* rp =
             reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0 + (long long)b * e.resid_bstride);
 #pragma unroll
@@ -93,7 +142,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    if (flags & EPI_RESID_LN) {
+    if (row_ok && (flags & EPI_RESID_LN)) {
         // residual = LayerNorm(pre-LN row) rebuilt from its saved statistics: saves the fp32 write + read of the
         // normalised residual stream (the LayerNorm kernel then only emits the 16-bit GEMM operand)
         const float4* rp = reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0);
@@ -112,18 +161,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         }
     }
     if (flags & EPI_OUT_F32) {
-        float4* op = reinterpret_cast<float4*>(e.out_f + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j * 4 < ncols) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        stage_put_f32(stage, v, lane);
+        stage_flush_f32(stage, e.out_f + woff, e.ldo, rows_valid, ncols, lane);
     }
     if (flags & EPI_OUT_H16) {
-        uint4* op = reinterpret_cast<uint4*>(e.out_h + off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j * 8 < ncols)
-                op[j] = make_uint4(pack_op(v[8 * j], v[8 * j + 1]), pack_op(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_op(v[8 * j + 4], v[8 * j + 5]), pack_op(v[8 * j + 6], v[8 * j + 7]));
+        stage_put_h16(reinterpret_cast<op_t*>(stage), v, lane);
+        stage_flush_h16(reinterpret_cast<op_t*>(stage), e.out_h + woff, e.ldo, rows_valid, ncols, lane);
     }
 }
 
@@ -131,7 +174,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, long long row, int col, int b) {
     const int flags = e.flags;
     if (flags & EPI_CDIST) {
-        const float d2 = e.norm_a[row] + e.norm_b[col] - 2.0f * v;
+        float d2 = e.norm_a[row] + e.norm_b[col] - 2.0f * (v * e.cd_inv_scale);
+        if (d2 < CD_REFINE) {
+            float s = 0.f;
+            for (int k = 0; k < 256; ++k) {
+                const float t = e.cd_a[row * 256 + k] - e.cd_b[(long long)col * 256 + k];
+                s = fmaf(t, t, s);
+            }
+            d2 = s;
+        }
         const float d = sqrtf(fmaxf(d2, 0.0f));
         if (e.out_f) e.out_f[row * e.ldo + col] = d;
         atomicAdd(e.row_sum + row, (double)d);
@@ -157,20 +208,77 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The TMEM load of chunk c+1 is in flight
-// while chunk c is processed, and the accumulator stage is handed back to the MMA warp as soon as the last load
-// has landed (before that chunk's math and stores).
+// Distance epilogue: d = sqrt(max(|a|^2 + |b|^2 - 2 a.b, 0)).  The Gram form cancels catastrophically for
+// near-duplicate rows, so squared distances below CD_REFINE are re-evaluated with fp32 direct differences
+// (rare); above it the fp32 Gram error (~2e-7 on d^2) keeps d within 3e-6 of scipy's float64 result.
+
+__device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
+                                              int rows_valid, int col0, int ncols, float* stage, int lane) {
+    const float na = row_ok ? __ldg(e.norm_a + row) : 0.f;
+    float s32 = 0.f;  // 32 distances <= 2 each: an fp32 partial sum is exact to ~1e-7; fp64 only across chunks
+    float nbv[32];
+    if (ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(e.norm_b + col0) + j);  // col0 % 32 == 0
+            nbv[4 * j] = t.x; nbv[4 * j + 1] = t.y; nbv[4 * j + 2] = t.z; nbv[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) nbv[j] = j < ncols ? __ldg(e.norm_b + col0 + j) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (row_ok && j < ncols) {
+            float d2 = na + nbv[j] - 2.0f * (v[j] * e.cd_inv_scale);
+            if (d2 < CD_REFINE) {
+                const float4* pa = reinterpret_cast<const float4*>(e.cd_a + row * 256);
+                const float4* pb = reinterpret_cast<const float4*>(e.cd_b + (long long)(col0 + j) * 256);
+                float s = 0.f;
+                for (int k = 0; k < 64; ++k) {
+                    const float4 x = __ldg(pa + k), y = __ldg(pb + k);
+                    const float d0 = x.x - y.x, d1 = x.y - y.y, d3 = x.z - y.z, d4 = x.w - y.w;
+                    s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d3, d3, s); s = fmaf(d4, d4, s);
+                }
+                d2 = s;
+            }
+            v[j] = sqrtf(fmaxf(d2, 0.f));
+            s32 += v[j];
+        }
+    }
+    const double rs = (double)s32;
+    if (e.out_f != nullptr) {  // warp-uniform
+        stage_put_f32(stage, v, lane);
+        float* wout = e.out_f + (row - lane) * e.ldo + col0;
+        if (ncols == 32 && (e.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(wout) & 15) == 0)) {
+            stage_flush_f32(stage, wout, e.ldo, rows_valid, ncols, lane);
+        } else {  // ragged / unaligned: one row per instruction, lane = column (still full-line coalesced)
+            __syncwarp();
+            for (int rl = 0; rl < 32 && rl < rows_valid; ++rl)
+                if (lane < ncols) wout[rl * e.ldo + lane] = stage[rl * 32 + ((((lane >> 2) ^ (rl & 7)) << 2) | (lane & 3))];
+            __syncwarp();
+        }
+    }
+    return rs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The accumulator stage is handed back
+// to the MMA warp as soon as the last TMEM load has landed (before that chunk's math and stores).
+// (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
 template <int CHUNKS, bool PAIR>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
-                                              int ccol_first, int b, uint64_t* tmem_empty_bar, int lane) {
-    uint32_t r[2][32];
-    tmem_ld_32x32(taddr, r[0]);
-#pragma unroll
+                                              int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage) {
+    const bool row_ok = row < args.M;
+    const long long rv = (long long)args.M - (row - lane);
+    const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
+    double row_sum = 0.0;
+#pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c + 1 < CHUNKS) {
-            tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-        } else {
+        if (c == CHUNKS - 1) {  // every TMEM read of this tile has landed: release the accumulator stage now
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -181,13 +289,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
         int ncols = args.N - col0;
         ncols = ncols > 32 ? 32 : ncols;
         if (ccol_first + c * 32 >= args.umma_n) ncols = 0;
-        if (row < args.M && ncols > 0) {
+        if (ncols > 0 && rows_valid > 0) {  // warp-uniform
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
-            epilogue_chunk(args.epi, v, row, col0, ncols, b);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (args.epi.flags & EPI_CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
+            else epilogue_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane);
         }
     }
+    if ((args.epi.flags & EPI_CDIST) && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -198,7 +308,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -308,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const long long row = (long long)m_blk * BM + q * 32 + lane;
             epilogue_tile<CHUNKS, false>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
-                                         row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane);
+                                         row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
         }
     }
     tc_fence_before();
@@ -331,8 +442,9 @@ struct Pair256 {
     static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows of A
     static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of B
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int STAGES = 5;
+    static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -342,7 +454,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -449,7 +562,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
             epilogue_tile<HALF / 32, true>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
-                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane);
+                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
         }
     }
     tc_fence_before();
@@ -659,7 +772,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         NB_CHECK(!(epi.flags & EPI_RESID) || (epi.ldr % 4 == 0 && epi.resid_bstride % 4 == 0),
                  "GEMM residual leading dimension must be a multiple of 4");
     }
-    if (impl == 1 || (epi.flags & EPI_CDIST)) {
+    if (impl == 1) {
         dim3 grid((N + 15) / 16, (M + 15) / 16, batch), block(16, 16);
         gemm_simt_kernel<<<grid, block, 0, st>>>(A, B, args);
         NB_LAUNCHED();

@@ -49,10 +49,13 @@ struct GemmEpilogue {
     op_t* out_h;
     long long ldo;
     long long out_bstride;
-    // EPI_CDIST
+    // EPI_CDIST: acc = cd_scale^-1 * <a_row, b_col> from split-fp16 operands
     const float* norm_a;      // [M] squared norms of the rows of A
     const float* norm_b;      // [N]
     double* row_sum;          // [M] += sum over cols of the distances
+    const float* cd_a;        // [M][256] original fp32 rows (exact re-evaluation of near-zero distances)
+    const float* cd_b;        // [N][256]
+    float cd_inv_scale;       // acc * cd_inv_scale = dot product
 };
 
 // C[b] = epilogue(A[b] (M x K) * B[b]^T (N x K)).  impl: 0 = tcgen05/TMA kernel, 1 = SIMT check kernel.

@@ -40,6 +40,9 @@ int launch_posconv(cudaStream_t st, const op_t* pos_g, long long rows_alloc, lon
 // ---- distance.cu
 int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
                       double* row_mean);
+size_t cdist_tc_workspace(long long n, long long m);
+int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
+                    double* row_mean, void* ws, size_t ws_bytes, int impl);
 
 __device__ __forceinline__ int find_utt_by_frame(const UttMeta* __restrict__ meta, int B, int f) {
     int lo = 0, hi = B - 1;

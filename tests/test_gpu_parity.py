@@ -216,7 +216,9 @@ def test_cdist_golden_and_properties(engine, golden_dir):
         ref = np.sqrt(((x[:, None, :].astype(np.float64) - y[None].astype(np.float64)) ** 2).sum(-1))
         assert np.abs(d.cpu().numpy() - ref).max() <= 1e-5
         assert np.abs(mu.cpu().numpy() - ref.mean(1)).max() <= 1e-5
-        np.testing.assert_array_equal(d.cpu().numpy(), dt.cpu().numpy().T)
+        # symmetry (bit-exact for the direct kernel; the split-fp16 Gram kernel sums its cross terms in a different
+        # order when the operands swap roles, so allow fp32 rounding there)
+        assert np.abs(d.cpu().numpy() - dt.cpu().numpy().T).max() <= 1e-6
     z, _ = engine.cdist_mean(a, a)
     assert float(z.diagonal().abs().max()) == 0.0
 
