@@ -266,7 +266,7 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The accumulator stage is handed back
 // to the MMA warp as soon as the last TMEM load has landed (before that chunk's math and stores).
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
-template <int CHUNKS, bool PAIR>
+template <int CHUNKS, bool PAIR, bool CDIST>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage) {
     const bool row_ok = row < args.M;
@@ -293,15 +293,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (args.epi.flags & EPI_CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
+            if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
             else epilogue_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane);
         }
     }
-    if ((args.epi.flags & EPI_CDIST) && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
+    if (CDIST && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool CDIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     using Cfg = TileCfg<BN>;
@@ -418,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * BM + q * 32 + lane;
-            epilogue_tile<CHUNKS, false>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
+            epilogue_tile<CHUNKS, false, CDIST>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
         }
     }
@@ -443,11 +443,11 @@ struct Pair256 {
     static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of B
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = 5;
-    static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+    static constexpr int smem_bytes(int epi_warps) { return STAGES * STAGE_BYTES + epi_warps * 4096 + 1024 + 256; }
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+template <int NEW, bool CDIST>  // NEW = epilogue warps (8 or 16)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     using Cfg = Pair256;
     constexpr int STAGES = Cfg::STAGES;
@@ -455,7 +455,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -480,7 +480,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);  // epilogue warps of BOTH CTAs arrive on the leader's
+            mbar_init(&tmem_empty[s], 2 * NEW);  // epilogue warps of BOTH CTAs arrive on the leader's
         }
         mbar_fence_init();
     }
@@ -550,7 +550,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ew = warp - 4;
         const int q = warp & 3;
         const int h = ew >> 2;
-        constexpr int HALF = BN / 2;
+        constexpr int HALF = BN / (NEW / 4);  // columns per epilogue warp (two or four column groups)
         int it = 0;
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
             const int n_blk = tile % args.n_tiles;
@@ -561,7 +561,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
-            epilogue_tile<HALF / 32, true>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+            epilogue_tile<HALF / 32, true, CDIST>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
         }
     }
@@ -709,12 +709,12 @@ static int prof_end(cudaStream_t st) {
     return 0;
 }
 
-template <int BN>
-static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+template <int BN, bool CDIST>
+static int launch_tc_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = TileCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -726,17 +726,23 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     int grid = device_sm_count();
     if (tiles < grid) grid = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
+    gemm_tc_kernel<BN, CDIST><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
 }
+template <int BN>
+static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
+}
 
-static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+template <int NEW, bool CDIST>
+static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
+    constexpr int SMEM = Cfg::smem_bytes(NEW);
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -749,10 +755,18 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_pair_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
+    gemm_tc_pair_kernel<NEW, CDIST><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
+}
+static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    if (args.epi.flags & EPI_CDIST) return launch_pair_impl<8, true>(st, A, B, args);
+    // 16 epilogue warps hide the latency of math-heavy (GELU) epilogues; NOMAD_B200_EPI16 overrides (0 / 1 / 2 = always)
+    static const int epi16 = getenv("NOMAD_B200_EPI16") ? atoi(getenv("NOMAD_B200_EPI16")) : 1;
+    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU)) != 0;
+    if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
+    return launch_pair_impl<8, false>(st, A, B, args);
 }
 
 int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
