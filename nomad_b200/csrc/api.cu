@@ -72,6 +72,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
     w.meta = (UttMeta*)take(sizeof(UttMeta) * p.B);
     w.stat_part = (double*)take(sizeof(double) * NSTAT * p.max_chunks * p.B);
     w.c0_fold = (float*)take(sizeof(float) * 12 * CONV_DIM * p.B);
+    w.c0_fold_h = (op_t*)take(2ull * 16 * CONV_DIM * p.B);
     w.gn_stat = save ? (float*)take(sizeof(float) * 2 * CONV_DIM * p.B) : nullptr;
     if (!save) {
         op_t* act_a = (op_t*)take(2ull * CONV_DIM * (p.rows0 + 8));
@@ -381,8 +382,9 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
     // conv0 + GroupNorm + GELU
     NB_TRY(launch_wave_stats(st, wav, ws.meta, p.B, p.max_chunks, ws.stat_part));
     NB_TRY(launch_gn_fold(st, ws.stat_part, ws.meta, p.B, p.max_chunks, w.conv0_w, w.gn_g, w.gn_b, ws.c0_fold,
-                          ws.gn_stat));
-    NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, p.rows0, ws.c0_fold, ws.y[0], ws.aux[0]));
+                          ws.gn_stat, ws.c0_fold_h));
+    NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, p.rows0, ws.c0_fold, impl == 0 ? ws.c0_fold_h : nullptr, ws.y[0],
+                              ws.aux[0]));
     // conv 1..6 as overlapping-row GEMMs over the flat channels-last activation
     for (int l = 1; l < 7; ++l) {
         const long long M = p.rows0 >> l;

@@ -1,6 +1,6 @@
 // Attention core on tcgen05 for utterances of at most 256 frames (<= 5.1 s; the bench workload has 199).
 //
-// One CTA (128 threads) = one (utterance, head, 128-query tile).  The whole key range fits one MMA:
+// One CTA (256 threads) = one (utterance, head, 128-query tile).  The whole key range fits one MMA:
 //   S = Q K^T     : tcgen05.mma M=128, N=Tp (T rounded up to 16, <= 256), K=64  -> 128 x Tp fp32 in TMEM
 //   softmax       : thread r owns query row r = TMEM lane r (two passes over the row straight from TMEM,
 //                   no cross-thread reduction), P written as fp16 into shared memory in the 128B-swizzled
@@ -18,7 +18,7 @@
 namespace nb {
 
 static constexpr int AT_MAXT = 256;
-static constexpr int AT_SMEM = 96 * 1024 + 1024 + 64;
+static constexpr int AT_SMEM = 96 * 1024 + 1024 + 64 + 2048;  // tiles + align slack + barriers + row reductions
 
 struct AttnTcArgs {
     const UttMeta* meta;
@@ -38,7 +38,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: thread (quarter = warp & 3, lane) owns query row quarter * 32 + lane = TMEM lane; the two
+// warps that share a TMEM lane quarter (warp and warp + 4) split the key columns between them (even / odd
+// 32-column chunks) and exchange row max / row sum through shared memory.
+__global__ void __launch_bounds__(256, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs args) {
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
     const UttMeta m = args.meta[b];
@@ -57,7 +60,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs 
     uint64_t* bar_s = bars + 1;         // S = QK^T done
     uint64_t* bar_o = bars + 2;         // O = PV done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    float* red = reinterpret_cast<float*>(smem + 98304 + 64);  // [2 halves][128 rows] max, then [2][128] sum
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int rowl = quarter * 32 + lane;  // local query row
 
     if (tid == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -95,43 +101,70 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs 
     mbar_wait(bar_s, 0);
     tc_fence_after();
 
-    // ---- softmax: this thread owns query row `tid` (TMEM lane tid)
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- softmax over this thread's chunks (half, half + 2, ...) of its row
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     const int chunks = (Tp + 31) >> 5;
     const float LOG2E = 1.4426950408889634f;
     float mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
+    {
+        // two register buffers, ping-ponged with static names so they stay in registers
+        uint32_t ra[32], rb[32];
+        auto scan = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
+        };
+        if (half < chunks) tmem_ld_32x32(trow + half * 32, ra);
+        for (int c = half; c < chunks; c += 4) {
+            tmem_ld_wait();
+            if (c + 2 < chunks) tmem_ld_32x32(trow + (c + 2) * 32, rb);
+            scan(ra, c);
+            if (c + 2 < chunks) {
+                tmem_ld_wait();
+                if (c + 4 < chunks) tmem_ld_32x32(trow + (c + 4) * 32, ra);
+                scan(rb, c + 2);
+            }
+        }
     }
+    red[half * 128 + rowl] = mx;
+    __syncthreads();
+    mx = fmaxf(red[rowl], red[128 + rowl]);
     float sum = 0.f;
     const float mscaled = mx * LOG2E;
-    for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
-        float p[32];
+    {
+        uint32_t ra[32], rb[32];
+        auto emit = [&](const uint32_t (&r)[32], int c) {
+            float p[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float e = ex2_approx(fmaf(__uint_as_float(r[j]), LOG2E, -mscaled));
-            p[j] = (c * 32 + j < T) ? e : 0.f;
-            sum += p[j];
-        }
-        // 32 keys = 4 chunks of 16 B in key block (c / 2), chunk index base (c & 1) * 4
-        const int kb = c >> 1;
-        uint8_t* pb = (kb < 3 ? smem + kb * 16384 : smem + 81920) + (tid >> 3) * 1024 + (tid & 7) * 128;
+            for (int j = 0; j < 32; ++j) {
+                const float e = ex2_approx(fmaf(__uint_as_float(r[j]), LOG2E, -mscaled));
+                p[j] = (c * 32 + j < T) ? e : 0.f;
+                sum += p[j];
+            }
+            // 32 keys = 4 pieces of 16 B in key block (c / 2), piece index base (c & 1) * 4
+            const int kb = c >> 1;
+            uint8_t* pb = (kb < 3 ? smem + kb * 16384 : smem + 81920) + (rowl >> 3) * 1024 + (rowl & 7) * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int ch = ((c & 1) * 4 + q) ^ (tid & 7);
-            *reinterpret_cast<uint4*>(pb + ch * 16) =
-                make_uint4(pack_op(p[8 * q], p[8 * q + 1]), pack_op(p[8 * q + 2], p[8 * q + 3]),
-                           pack_op(p[8 * q + 4], p[8 * q + 5]), pack_op(p[8 * q + 6], p[8 * q + 7]));
+            for (int q = 0; q < 4; ++q) {
+                const int ch = ((c & 1) * 4 + q) ^ (rowl & 7);
+                *reinterpret_cast<uint4*>(pb + ch * 16) =
+                    make_uint4(pack_op(p[8 * q], p[8 * q + 1]), pack_op(p[8 * q + 2], p[8 * q + 3]),
+                               pack_op(p[8 * q + 4], p[8 * q + 5]), pack_op(p[8 * q + 6], p[8 * q + 7]));
+            }
+        };
+        if (half < chunks) tmem_ld_32x32(trow + half * 32, ra);
+        for (int c = half; c < chunks; c += 4) {
+            tmem_ld_wait();
+            if (c + 2 < chunks) tmem_ld_32x32(trow + (c + 2) * 32, rb);
+            emit(ra, c);
+            if (c + 2 < chunks) {
+                tmem_ld_wait();
+                if (c + 4 < chunks) tmem_ld_32x32(trow + (c + 4) * 32, ra);
+                emit(rb, c + 2);
+            }
         }
     }
+    red[256 + half * 128 + rowl] = sum;
     // P (generic-proxy writes) must be visible to the tensor core (async proxy); S reads must be done
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -149,31 +182,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs 
         }
         umma_commit(bar_o);
     }
+    sum = red[256 + rowl] + red[384 + rowl];
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    const int q = q0 + tid;
-    const float inv = 1.0f / sum;
+    // ---- epilogue: this thread's 32 of the 64 output columns; staged through the (now dead) Q/K region so
+    // that every store instruction writes whole sectors
     {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(trow, r0);
-        tmem_ld_32x32(trow + 32, r1);
+        uint32_t r0[32];
+        tmem_ld_32x32(trow + half * 32, r0);
         tmem_ld_wait();
-        if (q < T) {
-            uint4* op = reinterpret_cast<uint4*>(args.out + ((long long)m.frame0 + q) * EMBED + h * HEAD_DIM);
+        const float inv = 1.0f / sum;
+        float v[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_op(__uint_as_float(r0[8 * j]) * inv, __uint_as_float(r0[8 * j + 1]) * inv),
-                                   pack_op(__uint_as_float(r0[8 * j + 2]) * inv, __uint_as_float(r0[8 * j + 3]) * inv),
-                                   pack_op(__uint_as_float(r0[8 * j + 4]) * inv, __uint_as_float(r0[8 * j + 5]) * inv),
-                                   pack_op(__uint_as_float(r0[8 * j + 6]) * inv, __uint_as_float(r0[8 * j + 7]) * inv));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                op[4 + j] = make_uint4(pack_op(__uint_as_float(r1[8 * j]) * inv, __uint_as_float(r1[8 * j + 1]) * inv),
-                                       pack_op(__uint_as_float(r1[8 * j + 2]) * inv, __uint_as_float(r1[8 * j + 3]) * inv),
-                                       pack_op(__uint_as_float(r1[8 * j + 4]) * inv, __uint_as_float(r1[8 * j + 5]) * inv),
-                                       pack_op(__uint_as_float(r1[8 * j + 6]) * inv, __uint_as_float(r1[8 * j + 7]) * inv));
-            if (args.lse != nullptr) args.lse[((long long)m.frame0 + q) * HEADS + h] = mx + __logf(sum);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) * inv;
+        op_t* stage = reinterpret_cast<op_t*>(smem + warp * 2048);
+        stage_put_h16(stage, v, lane);
+        const int rows_valid = T - (q0 + quarter * 32);
+        op_t* wout = args.out + ((long long)m.frame0 + q0 + quarter * 32) * EMBED + h * HEAD_DIM + half * 32;
+        stage_flush_h16(stage, wout, EMBED, rows_valid > 32 ? 32 : rows_valid, 32, lane);
+        if (args.lse != nullptr && half == 0 && q0 + rowl < T)
+            args.lse[((long long)m.frame0 + q0 + rowl) * HEADS + h] = mx + __logf(sum);
     }
     tc_fence_before();
     __syncthreads();
@@ -216,7 +244,7 @@ int launch_attention_tc(cudaStream_t st, const op_t* qkv, const UttMeta* meta, i
     AttnTcArgs a{meta, out, lse};
     const int mt = max_T > AT_MAXT ? AT_MAXT : max_T;
     dim3 grid((mt + 127) / 128, HEADS, B);
-    attention_tc_kernel<<<grid, 128, AT_SMEM, st>>>(tm, a);
+    attention_tc_kernel<<<grid, 256, AT_SMEM, st>>>(tm, a);
     NB_LAUNCHED();
     return 0;
 }

@@ -142,6 +142,50 @@ __device__ __forceinline__ float2 unpack_op(uint32_t u) {
     return __half22float2(v);
 }
 
+// ---------------------------------------------------------------- row-per-lane -> coalesced stores via smem
+static constexpr int STAGE_BYTES_PER_WARP = 4096;
+
+__device__ __forceinline__ void stage_put_f32(float* stage, const float (&v)[32], int lane) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        *reinterpret_cast<float4*>(stage + lane * 32 + ((p ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+}
+// out points at (first row of this warp, first column of the chunk)
+__device__ __forceinline__ void stage_flush_f32(const float* stage, float* out, long long ld, int rows_valid, int ncols,
+                                                int lane) {
+    __syncwarp();
+    const int p = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rl = k * 4 + (lane >> 3);
+        if (rl < rows_valid && p * 4 < ncols)
+            *reinterpret_cast<float4*>(out + rl * ld + p * 4) =
+                *reinterpret_cast<const float4*>(stage + rl * 32 + ((p ^ (rl & 7)) << 2));
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void stage_put_h16(op_t* stage, const float (&v)[32], int lane) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<uint4*>(stage + lane * 32 + ((p ^ ((lane >> 1) & 3)) << 3)) =
+            make_uint4(pack_op(v[8 * p], v[8 * p + 1]), pack_op(v[8 * p + 2], v[8 * p + 3]),
+                       pack_op(v[8 * p + 4], v[8 * p + 5]), pack_op(v[8 * p + 6], v[8 * p + 7]));
+}
+__device__ __forceinline__ void stage_flush_h16(const op_t* stage, op_t* out, long long ld, int rows_valid, int ncols,
+                                                int lane) {
+    __syncwarp();
+    const int p = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rl = k * 8 + (lane >> 2);
+        if (rl < rows_valid && p * 8 < ncols)
+            *reinterpret_cast<uint4*>(out + rl * ld + p * 8) =
+                *reinterpret_cast<const uint4*>(stage + rl * 32 + ((p ^ ((rl >> 1) & 3)) << 3));
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -8,6 +8,8 @@
 //     sum_t y^2    = sum_jj' w_j w_j' R_jj'    R_jj'  = sum_t x[5 t + j] x[5 t + j']
 // so one cheap pass over the waveform (65 sums per utterance, fp64) replaces a stats pass over the
 // 512-channel conv0 output, and normalisation folds into per-(utterance, channel) conv taps.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace nb {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
                                                       const UttMeta* __restrict__ meta, int max_chunks,
                                                       const float* __restrict__ w0, const float* __restrict__ gn_g,
                                                       const float* __restrict__ gn_b, float* __restrict__ fold,
-                                                      float* __restrict__ stat_out) {
+                                                      float* __restrict__ stat_out, op_t* __restrict__ fold_h) {
     const int b = blockIdx.x;
     const UttMeta m = meta[b];
     __shared__ double s[NSTAT];
@@ -104,6 +106,12 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
     for (int j = 0; j < 10; ++j) o[j] = (float)(w[j] * a);
     o[10] = (float)((double)gn_b[c] - mean * a);
     o[11] = (float)a;  // gamma * rstd, folded into the saved GELU gradient for the loss backward
+    if (fold_h != nullptr) {  // 16-bit taps, K padded to 16, for the tensor-core conv0 (B operand of mma.sync)
+        uint32_t* h = reinterpret_cast<uint32_t*>(fold_h + ((long long)b * CONV_DIM + c) * 16);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) h[j] = pack_op((float)(w[2 * j] * a), (float)(w[2 * j + 1] * a));
+        h[5] = 0u; h[6] = 0u; h[7] = 0u;
+    }
     if (stat_out != nullptr) {
         stat_out[((long long)b * CONV_DIM + c) * 2 + 0] = (float)mean;
         stat_out[((long long)b * CONV_DIM + c) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
@@ -111,8 +119,9 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
 }
 
 int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
-                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out) {
-    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold, stat_out);
+                   const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out,
+                   op_t* fold_h) {
+    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold, stat_out, fold_h);
     NB_LAUNCHED();
     return 0;
 }
@@ -216,8 +225,93 @@ int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core conv0: the 10-tap stride-5 conv as mma.sync m16n8k16 (fp16 in, fp32 accumulate):
+//   A[t][k] = x[5 t + k] (k < 16; taps 10..15 meet zero weights),  B[k][c] = folded taps (GroupNorm folded in).
+// One block = 64 frames x 512 channels, warp w owns channels [64 w, 64 w + 64).  The scalar kernel above spends
+// 20 of its ~27 instructions per element on FMAs and shared loads; here the FMAs are 32 mma per warp and what
+// remains is the GELU.  Lanes of a quad trade halves so every store instruction writes full 32 B sectors.
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
+                                                        int B, const float* __restrict__ fold,
+                                                        const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
+    const int row_base = blockIdx.x * C0_ROWS;
+    const int b = find_utt_by_frame(meta, B, blockIdx.x);
+    const UttMeta m = meta[b];
+    const int t_base = row_base - m.row0;
+    __shared__ float xs[C0_ROWS * 5 + 16];
+    const float* x = wav + m.wav_off;
+    for (int i = threadIdx.x; i < C0_ROWS * 5 + 16; i += blockDim.x) {
+        const long long s = (long long)t_base * 5 + i;
+        xs[i] = (s < m.n) ? __ldg(x + s) : 0.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, q = lane & 3;
+    // B fragments + shifts of this warp's 8 channel tiles
+    uint32_t bf[8][2];
+    float sh[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int cb = warp * 64 + nt * 8;
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cb + r) * 16);
+        bf[nt][0] = __ldg(h + q);
+        bf[nt][1] = __ldg(h + q + 4);
+        sh[nt][0] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q) * 12 + 10);
+        sh[nt][1] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q + 1) * 12 + 10);
+    }
+    __syncthreads();
+    const int valid = m.T0 - t_base;
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+        uint32_t af[4];
+        {
+            const int i0 = 5 * (mt * 16 + r) + 2 * q, i1 = i0 + 40;  // rows r and r + 8
+            af[0] = pack_op(xs[i0], xs[i0 + 1]);
+            af[1] = pack_op(xs[i1], xs[i1 + 1]);
+            af[2] = pack_op(xs[i0 + 8], xs[i0 + 9]);
+            af[3] = pack_op(xs[i1 + 8], xs[i1 + 9]);
+        }
+        const int row0 = mt * 16 + r, row1 = row0 + 8;
+        op_t* o0 = out + (long long)(row_base + row0) * CONV_DIM + warp * 64 + 4 * q;
+        op_t* o1 = out + (long long)(row_base + row1) * CONV_DIM + warp * 64 + 4 * q;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // pairs of channel tiles: 16 channels = 32 B per row per quad
+            float c0[4] = {sh[2 * np][0], sh[2 * np][1], sh[2 * np][0], sh[2 * np][1]};
+            float c1[4] = {sh[2 * np + 1][0], sh[2 * np + 1][1], sh[2 * np + 1][0], sh[2 * np + 1][1]};
+            mma_f16_16816(c0, af, bf[2 * np][0], bf[2 * np][1]);
+            mma_f16_16816(c1, af, bf[2 * np + 1][0], bf[2 * np + 1][1]);
+            // packed pairs: e = tile 2np (cols 2q, 2q+1), f = tile 2np+1, rows row0 / row1
+            uint32_t e0 = pack_op(gelu_erf(c0[0]), gelu_erf(c0[1])), e1 = pack_op(gelu_erf(c0[2]), gelu_erf(c0[3]));
+            uint32_t f0 = pack_op(gelu_erf(c1[0]), gelu_erf(c1[1])), f1 = pack_op(gelu_erf(c1[2]), gelu_erf(c1[3]));
+            // lane q stores channels 4q..4q+3 of the 16: q<2 -> from tile 2np lanes (2q, 2q+1); q>=2 -> tile 2np+1
+            const int src = (lane & ~3) | ((2 * q) & 3);
+            const uint32_t a_e0 = __shfl_sync(0xffffffffu, e0, src), b_e0 = __shfl_sync(0xffffffffu, e0, src + 1);
+            const uint32_t a_f0 = __shfl_sync(0xffffffffu, f0, src), b_f0 = __shfl_sync(0xffffffffu, f0, src + 1);
+            const uint32_t a_e1 = __shfl_sync(0xffffffffu, e1, src), b_e1 = __shfl_sync(0xffffffffu, e1, src + 1);
+            const uint32_t a_f1 = __shfl_sync(0xffffffffu, f1, src), b_f1 = __shfl_sync(0xffffffffu, f1, src + 1);
+            uint2 v0 = q < 2 ? make_uint2(a_e0, b_e0) : make_uint2(a_f0, b_f0);
+            uint2 v1 = q < 2 ? make_uint2(a_e1, b_e1) : make_uint2(a_f1, b_f1);
+            if (row0 >= valid) v0 = make_uint2(0u, 0u);
+            if (row1 >= valid) v1 = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(o0 + np * 16) = v0;
+            *reinterpret_cast<uint2*>(o1 + np * 16) = v1;
+        }
+    }
+}
+
 int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
-                       const float* fold, op_t* out, op_t* aux_out) {
+                       const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out) {
+    static const int use_mma = getenv("NOMAD_B200_CONV0_MMA") ? atoi(getenv("NOMAD_B200_CONV0_MMA")) : 1;
+    if (aux_out == nullptr && fold_h != nullptr && use_mma) {
+        conv0_mma_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, fold_h, out);
+        NB_LAUNCHED();
+        return 0;
+    }
     conv0_apply_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, out, aux_out);
     NB_LAUNCHED();
     return 0;

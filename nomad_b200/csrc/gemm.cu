@@ -47,49 +47,6 @@ struct GemmArgs {
 // shared-memory staging buffer (32 rows x 128 B, 16-byte pieces XOR-swizzled): lanes deposit their row, then
 // the warp reads it back transposed so that consecutive lanes store consecutive 16 B of the SAME row --
 // full 32 B sectors / 128 B lines per instruction.
-static constexpr int STAGE_BYTES_PER_WARP = 4096;
-
-__device__ __forceinline__ void stage_put_f32(float* stage, const float (&v)[32], int lane) {
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-        *reinterpret_cast<float4*>(stage + lane * 32 + ((p ^ (lane & 7)) << 2)) =
-            make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
-}
-// out points at (first row of this warp, first column of the chunk)
-__device__ __forceinline__ void stage_flush_f32(const float* stage, float* out, long long ld, int rows_valid, int ncols,
-                                                int lane) {
-    __syncwarp();
-    const int p = lane & 7;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int rl = k * 4 + (lane >> 3);
-        if (rl < rows_valid && p * 4 < ncols)
-            *reinterpret_cast<float4*>(out + rl * ld + p * 4) =
-                *reinterpret_cast<const float4*>(stage + rl * 32 + ((p ^ (rl & 7)) << 2));
-    }
-    __syncwarp();
-}
-__device__ __forceinline__ void stage_put_h16(op_t* stage, const float (&v)[32], int lane) {
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-        *reinterpret_cast<uint4*>(stage + lane * 32 + ((p ^ ((lane >> 1) & 3)) << 3)) =
-            make_uint4(pack_op(v[8 * p], v[8 * p + 1]), pack_op(v[8 * p + 2], v[8 * p + 3]),
-                       pack_op(v[8 * p + 4], v[8 * p + 5]), pack_op(v[8 * p + 6], v[8 * p + 7]));
-}
-__device__ __forceinline__ void stage_flush_h16(const op_t* stage, op_t* out, long long ld, int rows_valid, int ncols,
-                                                int lane) {
-    __syncwarp();
-    const int p = lane & 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int rl = k * 8 + (lane >> 2);
-        if (rl < rows_valid && p * 8 < ncols)
-            *reinterpret_cast<uint4*>(out + rl * ld + p * 8) =
-                *reinterpret_cast<const uint4*>(stage + rl * 32 + ((p ^ ((rl >> 1) & 3)) << 3));
-    }
-    __syncwarp();
-}
-
 // Epilogue for one warp x 32-column chunk: lane owns row `row` (v[] = its fp32 accumulators).  Executed by all
 // 32 lanes (staging is warp-collective); lanes whose row is past M skip the loads and are never flushed.
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
@@ -762,9 +719,11 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
 }
 static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     if (args.epi.flags & EPI_CDIST) return launch_pair_impl<8, true>(st, A, B, args);
-    // 16 epilogue warps hide the latency of math-heavy (GELU) epilogues; NOMAD_B200_EPI16 overrides (0 / 1 / 2 = always)
+    // 16 epilogue warps hide the latency of a math-heavy (GELU) epilogue when the mainloop is short (FC1, K = 768:
+    // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
+    // NOMAD_B200_EPI16 overrides (0 = never, 2 = always).
     static const int epi16 = getenv("NOMAD_B200_EPI16") ? atoi(getenv("NOMAD_B200_EPI16")) : 1;
-    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU)) != 0;
+    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU)) != 0 && args.K <= 1024;
     if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
