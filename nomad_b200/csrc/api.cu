@@ -1,5 +1,6 @@
 // Handle, weight preparation, batch planning and the forward pass behind the C ABI.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -55,6 +56,7 @@ int make_plan(const int64_t* off, int B, Plan* p) {
     p->frames = row / 64;
     p->pos_rows = p->frames + (long long)POS_K * B + POS_K / 2;
     p->max_chunks = (max_T0 + STAT_CHUNK - 1) / STAT_CHUNK;
+    build_attention_items(*p, &p->attn_items);
     return 0;
 }
 
@@ -70,6 +72,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
     w.save = save;
     const size_t F = (size_t)p.frames;
     w.meta = (UttMeta*)take(sizeof(UttMeta) * p.B);
+    w.attn_items = (uint32_t*)take(sizeof(uint32_t) * p.attn_items.size());
     w.stat_part = (double*)take(sizeof(double) * NSTAT * p.max_chunks * p.B);
     w.c0_fold = (float*)take(sizeof(float) * 12 * CONV_DIM * p.B);
     w.c0_fold_h = (op_t*)take(2ull * 16 * CONV_DIM * p.B);
@@ -333,15 +336,17 @@ static int build_weights(Handle* h, TensorTable& tt) {
 // Forward pass
 static constexpr int META_SLOTS = 4;
 
-int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st) {
+int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st) {
     static thread_local int slot = 0;
-    if (h->meta_cap < p.B) {
+    const size_t meta_bytes = sizeof(UttMeta) * p.B, item_bytes = sizeof(uint32_t) * p.attn_items.size();
+    const size_t need = align_up(meta_bytes, 64) + item_bytes;
+    if (h->meta_cap < need) {
         if (h->meta_host) {
             NB_CUDA(cudaDeviceSynchronize());
             NB_CUDA(cudaFreeHost(h->meta_host));
         }
-        h->meta_cap = p.B < 1024 ? 1024 : p.B * 2;
-        NB_CUDA(cudaMallocHost((void**)&h->meta_host, sizeof(UttMeta) * h->meta_cap * META_SLOTS));
+        h->meta_cap = need < (64u << 10) ? (64u << 10) : need * 2;
+        NB_CUDA(cudaMallocHost((void**)&h->meta_host, h->meta_cap * META_SLOTS));
     }
     if (!h->meta_event) {
         // one event per slot, stored contiguously
@@ -352,9 +357,11 @@ int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st) {
     cudaEvent_t* ev = (cudaEvent_t*)(void*)h->meta_event;
     slot = (slot + 1) % META_SLOTS;
     NB_CUDA(cudaEventSynchronize(ev[slot]));  // no-op unless this slot's previous copy is still in flight
-    UttMeta* stage = h->meta_host + (size_t)slot * h->meta_cap;
-    memcpy(stage, p.utt.data(), sizeof(UttMeta) * p.B);
-    NB_CUDA(cudaMemcpyAsync(dev, stage, sizeof(UttMeta) * p.B, cudaMemcpyHostToDevice, st));
+    char* stage = h->meta_host + (size_t)slot * h->meta_cap;
+    memcpy(stage, p.utt.data(), meta_bytes);
+    memcpy(stage + align_up(meta_bytes, 64), p.attn_items.data(), item_bytes);
+    NB_CUDA(cudaMemcpyAsync(ws.meta, stage, meta_bytes, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(ws.attn_items, stage + align_up(meta_bytes, 64), item_bytes, cudaMemcpyHostToDevice, st));
     NB_CUDA(cudaEventRecord(ev[slot], st));
     return 0;
 }
@@ -439,8 +446,14 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             NB_TRY(gemm_h16(st, A, Bw, (int)F, 3 * EMBED, EMBED, 1, e, impl));
         }
         if (impl == 0) {
-            NB_TRY(launch_attention_tc(st, Lb.qkv, ws.meta, p.B, p.max_T, F, Lb.attn, Lb.lse));
-            if (p.max_T > 256) NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 256));
+            static const int attn_sel = getenv("NOMAD_B200_ATTN") ? atoi(getenv("NOMAD_B200_ATTN")) : 0;
+            if (attn_sel == 1) {  // previous generation: one-shot tcgen05 kernel (T <= 256) + streaming mma.sync kernel
+                NB_TRY(launch_attention_tc(st, Lb.qkv, ws.meta, p.B, p.max_T, F, Lb.attn, Lb.lse));
+                if (p.max_T > 256) NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 256));
+            } else {
+                NB_TRY(launch_attention_fa(st, Lb.qkv, ws.meta, ws.attn_items, (int)p.attn_items.size(), F, Lb.attn,
+                                           Lb.lse));
+            }
         } else {
             NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 0));
         }
@@ -592,7 +605,7 @@ int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t*
     NB_CHECK(workspace_bytes >= need, "embed: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "embed: workspace must be 1024-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    NB_TRY(upload_meta(h, p, ws.meta, st));
+    NB_TRY(upload_meta(h, p, ws, st));
     NB_TRY(forward_encoder(h, p, ws, wav_dev, st, nullptr, 0));
     NB_TRY(launch_pool_head(st, ws.x, ws.meta, p.B, h->w.head_wt, h->w.head_b, emb_dev, nullptr));
     return 0;
@@ -659,7 +672,7 @@ int nomad_b200_layers_fwd(nomad_b200_handle* hh, const float* wav_dev, int B, in
     const size_t need = carve_workspace(p, workspace_dev, &ws, false);
     NB_CHECK(workspace_bytes >= need, "layers_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    NB_TRY(upload_meta(h, p, ws.meta, st));
+    NB_TRY(upload_meta(h, p, ws, st));
     NB_TRY(forward_encoder(h, p, ws, wav_dev, st, layers_dev, p.max_T));
     if (emb_dev) {
         const bool lh = h->has_loss_head;

@@ -586,7 +586,7 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
     NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "loss: workspace must be 1024-byte aligned");
 
     // ------------------------------------------------------------------ forward (both halves, save mode)
-    NB_TRY(upload_meta(h, p, ws.meta, st));
+    NB_TRY(upload_meta(h, p, ws, st));
     NB_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * 16, st));
     NB_TRY(forward_encoder(h, p, ws, est_dev, st, nullptr, 0));
     NB_TRY(launch_pool_head(st, ws.x, ws.meta, p.B, w.loss_head_wt, w.loss_head_b, L.emb, L.pooled));

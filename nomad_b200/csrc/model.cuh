@@ -76,6 +76,7 @@ struct Plan {
     int max_T = 0;
     int max_chunks = 0;    // wave-stats chunks of the longest utterance
     bool uniform = false;  // all utterances the same length
+    std::vector<uint32_t> attn_items;  // (utterance << 8) | query tile, longest utterances first (attention_fa.cu)
 };
 
 // Device pointers carved from the caller's workspace for one forward pass.  In scoring mode the conv
@@ -93,6 +94,7 @@ struct LayerBufs {
 struct Workspace {
     bool save;
     UttMeta* meta;       // [B]
+    uint32_t* attn_items;  // [Plan::attn_items.size()] work list of the attention kernel
     double* stat_part;   // [B][max_chunks][65]
     float* c0_fold;      // [B][512][12]: 10 folded taps, shift, gamma * rstd
     op_t* c0_fold_h;     // [B][512][16]: the folded taps as 16-bit, K padded to 16 (tensor-core conv0)
@@ -118,8 +120,8 @@ struct Handle {
     Weights w{};
     std::vector<void*> allocs;  // everything cudaMalloc'ed for the weights
     bool has_loss_head = false;
-    UttMeta* meta_host = nullptr;  // pinned staging for the per-call metadata
-    int meta_cap = 0;
+    char* meta_host = nullptr;  // pinned staging for the per-call metadata (UttMeta[B] + attention work list)
+    size_t meta_cap = 0;        // bytes per staging slot
     cudaEvent_t meta_event = nullptr;  // last use of meta_host by an async copy
 };
 
@@ -127,7 +129,8 @@ int make_plan(const int64_t* sample_offsets, int B, Plan* plan);
 size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save);
 int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st, float* layers_out,
                     int layer_T);
-int upload_meta(Handle* h, const Plan& p, UttMeta* dev, cudaStream_t st);
+int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st);
+void build_attention_items(const Plan& p, std::vector<uint32_t>* items);
 GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld);
 
 }  // namespace nb
