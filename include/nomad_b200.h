@@ -116,6 +116,17 @@ NOMAD_B200_API int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_
                          const float* bias, const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags,
                          int gemm_impl, void* stream);
 
+/* The attention core of one encoder layer, softmax(Q K^T) V per (utterance, head) (fairseq
+ * MultiheadAttention inside TransformerSentenceEncoderLayer; mirror torchaudio components.py:237-330).
+ * qkv: frames x 2304 op_t device (q | k | v per row, q already scaled by head_dim^-0.5); utterance u owns rows
+ * [frame0[u], frame0[u] + T[u]) (HOST arrays).  out: frames x 768 op_t device (rows of valid frames are written);
+ * lse: frames x 12 fp32 device (log-sum-exp of each softmax row, used by the loss backward) or NULL.
+ * workspace: device scratch for the kernel's work list. */
+NOMAD_B200_API size_t nomad_b200_attention_workspace_bytes(const int32_t* T, int n_utts);
+NOMAD_B200_API int nomad_b200_attention_f16(const void* qkv_f16, int64_t frames, const int32_t* frame0, const int32_t* T,
+                             int n_utts, void* out_f16, float* lse, void* workspace_dev, size_t workspace_bytes,
+                             void* stream);
+
 /* In-situ timing of the tensor-core GEMM launches (one CUDA event pair per launch, on the launching
  * stream) for the roofline leg of bench.py: enable, run steps, read the summed device time (ms), the
  * algorithmic FLOPs (2*M*N*K) and the launch count; reading synchronises on the recorded events. */

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnomad_b200.so")
+LIB_PATH = os.environ.get("NOMAD_B200_LIB") or os.path.join(_HERE, "csrc", "libnomad_b200.so")  # override: kernel A/B probes
 
 c_i64 = C.c_int64
 c_vp = C.c_void_p
@@ -42,6 +42,9 @@ PROTOTYPES = {
     "nomad_b200_cdist_mean_host": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
     "nomad_b200_gemm_f16": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
+    "nomad_b200_attention_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_int32), C.c_int]),
+    "nomad_b200_attention_f16": (C.c_int, [c_vp, c_i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, c_vp, c_vp,
+                                            c_vp, C.c_size_t, c_vp]),
     "nomad_b200_profile_gemm": (C.c_int, [C.c_int]),
     "nomad_b200_profile_gemm_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "nomad_b200_launch_count": (c_i64, []),

@@ -451,7 +451,7 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
                 NB_TRY(launch_attention_tc(st, Lb.qkv, ws.meta, p.B, p.max_T, F, Lb.attn, Lb.lse));
                 if (p.max_T > 256) NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 256));
             } else {
-                NB_TRY(launch_attention_fa(st, Lb.qkv, ws.meta, ws.attn_items, (int)p.attn_items.size(), F, Lb.attn,
+                NB_TRY(launch_attention_fa(st, Lb.qkv, ws.attn_items, (int)(p.attn_items.size() / 4), F, Lb.attn,
                                            Lb.lse));
             }
         } else {
@@ -634,6 +634,34 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
     NB_CUDA(cudaMemcpyAsync(emb_host, emb_dev, (size_t)B * EMB * 4, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+size_t nomad_b200_attention_workspace_bytes(const int32_t* T, int n_utts) {
+    size_t entries = 0;
+    for (int u = 0; T != nullptr && u < n_utts; ++u) entries += (size_t)((T[u] + 127) / 128);
+    return entries * 16 + 1024;
+}
+
+int nomad_b200_attention_f16(const void* qkv_f16, int64_t frames, const int32_t* frame0, const int32_t* T, int n_utts,
+                             void* out_f16, float* lse, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_CHECK(qkv_f16 && frame0 && T && out_f16 && workspace_dev && n_utts > 0 && frames > 0, "attention: bad arguments");
+    Plan p;
+    p.B = n_utts;
+    p.utt.resize(n_utts);
+    for (int u = 0; u < n_utts; ++u) {
+        NB_CHECK(T[u] >= 1 && frame0[u] >= 0 && (int64_t)frame0[u] + T[u] <= frames, "attention: utterance %d out of range", u);
+        memset(&p.utt[u], 0, sizeof(UttMeta));
+        p.utt[u].T = T[u];
+        p.utt[u].frame0 = frame0[u];
+    }
+    std::vector<uint32_t> items;
+    build_attention_items(p, &items);
+    NB_CHECK(workspace_bytes >= items.size() * 4, "attention: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_CUDA(cudaMemcpyAsync(workspace_dev, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaStreamSynchronize(st));  // items is a pageable temporary
+    return launch_attention_fa(st, (const op_t*)qkv_f16, (const uint32_t*)workspace_dev, (int)(items.size() / 4), frames,
+                               (op_t*)out_f16, lse);
 }
 
 int64_t nomad_b200_num_frames(int64_t n) {

@@ -1,19 +1,22 @@
 // Attention core softmax(Q K^T) V on tcgen05 for utterances of ANY length (non-causal, keys >= T masked).
 // q is already scaled by head_dim^-0.5 (folded into the QKV weights).
 //
-// Work item = (utterance, head, 128-query tile).  A persistent CTA (192 threads, two CTAs per SM) walks a
-// host-built item list (longest utterances first) and streams 128-key tiles through a 3-stage TMA ring:
-//   warp 0 (one lane)  TMA producer: Q tile, then K_0, V_0, K_1, V_1, ... (16 KB boxes, 128B swizzle)
-//   warp 1 (one lane)  MMA issuer:   S = Q K_j^T      tcgen05.mma M=128 N=128 K=64 -> TMEM columns [0, 128)
-//                                    O (+)= P_j V_j   tcgen05.mma M=128 N=64  K<=128 -> TMEM columns [128, 192)
+// Work item = (utterance, head, 128-query tile).  A persistent CTA (192 threads, THREE CTAs per SM: 64 KB of
+// shared memory, 128 TMEM columns, <= 112 registers) walks a host-built item list (longest utterances first)
+// and streams 64-key tiles through a 4-stage TMA ring:
+//   warp 0 (one lane)  TMA producer: Q tile (16 KB), then K_0, V_0, K_1, V_1, ... (8 KB boxes, 128B swizzle)
+//   warp 1 (one lane)  MMA issuer:   S = Q K_j^T      tcgen05.mma M=128 N=64 K=64  -> TMEM columns [0, 64)
+//                                    O (+)= P_j V_j   tcgen05.mma M=128 N=64 K<=64 -> TMEM columns [64, 128)
 //                                    (V in its natural [key][d] layout as an MN-major B operand)
 //   warps 2..5         softmax: thread r owns query row r = TMEM lane r.  Per key tile: row max straight from
 //                      TMEM, online-softmax rescale of the O row in TMEM (only when some row of the warp saw a
 //                      new maximum), P = exp2(.) as fp16 into shared memory in the K-major swizzled operand
 //                      layout; after the last tile O / rowsum -> fp16 -> staged, sector-aligned global stores.
-// Per CTA the chain S-MMA -> softmax -> PV-MMA is serial in the key tiles (S is single-buffered: 192 of the
-// CTA's 256 TMEM columns); the second CTA on the SM fills the gaps, and the TMA producer runs ahead across
-// items so loads never sit on the critical path.
+// Per CTA the chain S-MMA -> softmax -> PV-MMA is serial in the key tiles (S is single-buffered).  The kernel is
+// bound by instruction issue in the softmax warps (ncu: ~9 instructions per score, IPC ~0.45 with two warps
+// per scheduler), not by the MMAs or their latency -- double/triple-buffered S, lazy rescaling and deferred
+// epilogues were all measured and bought nothing (profiles/r01_attention_notes.md) -- so the design goes for
+// occupancy instead: small tiles let three CTAs (12 softmax warps) share an SM and fill each other's gaps.
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -23,21 +26,33 @@
 namespace nb {
 
 static constexpr int FA_THREADS = 192;
-static constexpr int FA_RING = 3;
-static constexpr int FA_TILE_BYTES = 16384;                       // 128 rows x 128 B
-static constexpr int FA_OFF_RING = FA_TILE_BYTES;                 // after Q
+static constexpr int FA_BK = 64;                                  // keys per tile
+static constexpr int FA_CHUNKS = FA_BK / 32;
+static constexpr int FA_RING = 4;
+static constexpr int FA_Q_BYTES = 16384;                          // 128 rows x 128 B
+static constexpr int FA_TILE_BYTES = FA_BK * 128;                 // K or V tile: FA_BK rows x 128 B
+static constexpr int FA_P_BYTES = (FA_BK / 64) * 16384;           // P = 64-key blocks of 128 rows x 128 B
+static constexpr int FA_OFF_RING = FA_Q_BYTES;                    // after Q
 static constexpr int FA_OFF_P = FA_OFF_RING + FA_RING * FA_TILE_BYTES;
-static constexpr int FA_OFF_BAR = FA_OFF_P + 2 * FA_TILE_BYTES;   // P = two 64-key blocks of 128 rows x 128 B
+static constexpr int FA_OFF_BAR = FA_OFF_P + FA_P_BYTES;
 static constexpr int FA_SMEM = FA_OFF_BAR + 128 + 1024;           // barriers + alignment slack
-static constexpr uint32_t FA_TMEM_COLS = 256;
-static constexpr uint32_t FA_O_COL = 128;
+static constexpr uint32_t FA_TMEM_COLS = 128;
+static constexpr uint32_t FA_O_COL = FA_BK;
+static constexpr int FA_CTAS_PER_SM = 3;
+
+// One (utterance, query tile) of the work list; every entry stands for HEADS work items.
+struct FaEntry {
+    int frame0;  // first row of the utterance in the frame-level buffers
+    int T;       // valid frames
+    int q0;      // first query row of the tile
+    int utt;
+};
 
 struct AttnFaArgs {
-    const UttMeta* meta;
-    const uint32_t* items;  // (utterance << 8) | query tile, longest utterances first
-    int n_items;            // entries of items; work items = n_items * HEADS
-    op_t* out;              // frames x 768
-    float* lse;             // frames x 12 or nullptr
+    const FaEntry* items;  // longest utterances first
+    int n_items;           // entries of items; work items = n_items * HEADS
+    op_t* out;             // frames x 768
+    float* lse;            // frames x 12 or nullptr
 };
 
 __device__ __forceinline__ uint32_t fa_idesc(int m, int n, int b_mn_major) {
@@ -64,24 +79,23 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct FaItem {
-    int b, h, q0, T, n_kv;
+    int h, q0, T, n_kv;
     long long frame0;
 };
 __device__ __forceinline__ FaItem fa_item(const AttnFaArgs& a, int i) {
-    const uint32_t e = __ldg(a.items + i / HEADS);
+    const int4 e = __ldg(reinterpret_cast<const int4*>(a.items) + i / HEADS);
     FaItem it;
-    it.b = (int)(e >> 8);
     it.h = i % HEADS;
-    it.q0 = (int)(e & 255u) * 128;
-    const UttMeta m = a.meta[it.b];
-    it.T = m.T;
-    it.n_kv = (m.T + 127) >> 7;
-    it.frame0 = m.frame0;
+    it.frame0 = e.x;
+    it.T = e.y;
+    it.q0 = e.z;
+    it.n_kv = (e.y + FA_BK - 1) / FA_BK;
     return it;
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
-attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs args) {
+__global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
+attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
+                    const AttnFaArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -103,6 +117,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
 
     if (tid == 0) {
         tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmKV);
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
         for (int s = 0; s < FA_RING; ++s) {
@@ -131,7 +146,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
             for (int i = blockIdx.x; i < total; i += gridDim.x, ++it) {
                 const FaItem w = fa_item(args, i);
                 mbar_wait(q_empty, (it & 1) ^ 1);
-                mbar_expect_tx(q_full, FA_TILE_BYTES);
+                mbar_expect_tx(q_full, FA_Q_BYTES);
                 fa_tma_2d(sQ, &tmQKV, q_full, w.h * HEAD_DIM, (int)w.frame0 + w.q0);
                 for (int j = 0; j < w.n_kv; ++j) {
 #pragma unroll
@@ -139,8 +154,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
                         const uint32_t st = c % FA_RING, ph = (c / FA_RING) & 1;
                         mbar_wait(&empty[st], ph ^ 1);
                         mbar_expect_tx(&full[st], FA_TILE_BYTES);
-                        fa_tma_2d(sRing + st * FA_TILE_BYTES, &tmQKV, &full[st], (1 + kv) * EMBED + w.h * HEAD_DIM,
-                                  (int)w.frame0 + j * 128);
+                        fa_tma_2d(sRing + st * FA_TILE_BYTES, &tmKV, &full[st], (1 + kv) * EMBED + w.h * HEAD_DIM,
+                                  (int)w.frame0 + j * FA_BK);
                     }
                 }
             }
@@ -148,7 +163,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t id_s = fa_idesc(128, 128, 0);
+            const uint32_t id_s = fa_idesc(128, FA_BK, 0);
             const uint32_t id_o = fa_idesc(128, HEAD_DIM, 1);  // B = V is MN-major: [key][d], d contiguous
             const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
             uint32_t c = 0, it = 0, g = 0;
@@ -157,11 +172,11 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
                 mbar_wait(&full[st], ph);
                 if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);
                 tc_fence_after();
-                const int nv = min(128, w.T - j * 128);
+                const int nv = min(FA_BK, w.T - j * FA_BK);
                 const int ksteps = ((nv + 31) >> 5) * 2;  // the softmax writes whole 32-key chunks (masked keys as 0)
                 const uint32_t vbase = smem_u32(sRing + st * FA_TILE_BYTES);
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t dp = umma_desc_sw128(smem_u32(sP) + (ks >> 2) * FA_TILE_BYTES) + (uint64_t)(2 * (ks & 3));
+                    const uint64_t dp = umma_desc_sw128(smem_u32(sP) + (ks >> 2) * 16384) + (uint64_t)(2 * (ks & 3));
                     const uint64_t dv = umma_desc_sw128(vbase + ks * 2048);  // 16 keys = two 8-row groups
                     umma_f16(tmem + FA_O_COL, dp, dv, id_o, (j | ks) ? 1u : 0u);
                 }
@@ -205,7 +220,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
             const bool active = rows_valid > 0;                  // warp-uniform
             float m_run = -INFINITY, l_run = 0.f;
             for (int j = 0; j < w.n_kv; ++j, ++g) {
-                const int nv = min(128, w.T - j * 128);
+                const int nv = min(FA_BK, w.T - j * FA_BK);
                 const int chunks = (nv + 31) >> 5;
                 mbar_wait(s_full, g & 1);
                 tc_fence_after();
@@ -267,7 +282,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
                             }
                         }
                         // 32 keys = 4 pieces of 16 B in key block (c / 2), piece index base (c & 1) * 4
-                        uint8_t* pb = prow + (c >> 1) * FA_TILE_BYTES;
+                        uint8_t* pb = prow + (c >> 1) * 16384;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int ch = ((c & 1) * 4 + q) ^ (rowl & 7);
@@ -320,7 +335,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFaArgs 
     }
 }
 
-// (utterance, query tile) pairs, longest utterances first so the static round-robin over persistent CTAs
+// (utterance, query tile) entries (4 words each, see FaEntry), longest utterances first so the static round-robin over persistent CTAs
 // behaves like longest-processing-time-first scheduling.
 void build_attention_items(const Plan& p, std::vector<uint32_t>* items) {
     std::vector<int> order(p.B);
@@ -329,7 +344,12 @@ void build_attention_items(const Plan& p, std::vector<uint32_t>* items) {
     items->clear();
     for (int b : order) {
         const int qt = (p.utt[b].T + 127) / 128;
-        for (int q = 0; q < qt; ++q) items->push_back(((uint32_t)b << 8) | (uint32_t)q);
+        for (int q = 0; q < qt; ++q) {  // one FaEntry = 4 words
+            items->push_back((uint32_t)p.utt[b].frame0);
+            items->push_back((uint32_t)p.utt[b].T);
+            items->push_back((uint32_t)(q * 128));
+            items->push_back((uint32_t)b);
+        }
     }
 }
 
@@ -337,7 +357,7 @@ typedef CUresult (*EncodeTiledFnFa)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int launch_attention_fa(cudaStream_t st, const op_t* qkv, const UttMeta* meta, const uint32_t* items, int n_items,
+int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items, int n_items,
                         long long frames, op_t* out, float* lse) {
     static EncodeTiledFnFa fn = nullptr;
     static std::once_flag once;
@@ -355,20 +375,22 @@ int launch_attention_fa(cudaStream_t st, const op_t* qkv, const UttMeta* meta, c
         attr_set = true;
     }
     if (n_items <= 0) return 0;
-    CUtensorMap tm;
+    CUtensorMap tmq, tmkv;
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * EMBED), (cuuint64_t)frames};
     cuuint64_t gstr[1] = {(cuuint64_t)(3 * EMBED) * 2};
-    cuuint32_t box[2] = {64, 128};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<op_t*>(qkv), gdim, gstr, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NB_CHECK(r == CUDA_SUCCESS, "attention: tensor map failed (%d)", (int)r);
-    AttnFaArgs a{meta, items, n_items, out, lse};
+    for (int k = 0; k < 2; ++k) {
+        cuuint32_t box[2] = {64, k == 0 ? 128u : (cuuint32_t)FA_BK};
+        CUresult r = fn(k == 0 ? &tmq : &tmkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<op_t*>(qkv), gdim, gstr,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NB_CHECK(r == CUDA_SUCCESS, "attention: tensor map failed (%d)", (int)r);
+    }
+    AttnFaArgs a{reinterpret_cast<const FaEntry*>(items), n_items, out, lse};
     const long long total = (long long)n_items * HEADS;
-    int grid = 2 * device_sm_count();
+    int grid = FA_CTAS_PER_SM * device_sm_count();
     if (total < grid) grid = (int)total;
-    attention_fa_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tm, a);
+    attention_fa_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmq, tmkv, a);
     NB_LAUNCHED();
     return 0;
 }

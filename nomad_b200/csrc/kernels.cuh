@@ -32,7 +32,7 @@ int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int 
 int launch_attention_tc(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, long long frames,
                         op_t* out, float* lse);
 // attention_fa.cu: persistent tcgen05 flash attention over the plan's work list (any T)
-int launch_attention_fa(cudaStream_t st, const op_t* qkv, const UttMeta* meta, const uint32_t* items, int n_items,
+int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items, int n_items,
                         long long frames, op_t* out, float* lse);
 int launch_pool_head(cudaStream_t st, const float* x, const UttMeta* meta, int B, const float* head_wt,
                      const float* head_b, float* emb, float* pooled_out);

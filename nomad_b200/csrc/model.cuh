@@ -76,7 +76,7 @@ struct Plan {
     int max_T = 0;
     int max_chunks = 0;    // wave-stats chunks of the longest utterance
     bool uniform = false;  // all utterances the same length
-    std::vector<uint32_t> attn_items;  // (utterance << 8) | query tile, longest utterances first (attention_fa.cu)
+    std::vector<uint32_t> attn_items;  // 4 words per (utterance, query tile), longest utterances first (attention_fa.cu)
 };
 
 // Device pointers carved from the caller's workspace for one forward pass.  In scoring mode the conv
