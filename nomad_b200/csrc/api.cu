@@ -75,7 +75,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
     w.attn_items = (uint32_t*)take(sizeof(uint32_t) * p.attn_items.size());
     w.stat_part = (double*)take(sizeof(double) * NSTAT * p.max_chunks * p.B);
     w.c0_fold = (float*)take(sizeof(float) * 12 * CONV_DIM * p.B);
-    w.c0_fold_h = (op_t*)take(2ull * 16 * CONV_DIM * p.B);
+    w.c0_fold_h = (op_t*)take(2ull * 32 * CONV_DIM * p.B);
     w.gn_stat = save ? (float*)take(sizeof(float) * 2 * CONV_DIM * p.B) : nullptr;
     if (!save) {
         op_t* act_a = (op_t*)take(2ull * CONV_DIM * (p.rows0 + 8));

@@ -106,11 +106,19 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
     for (int j = 0; j < 10; ++j) o[j] = (float)(w[j] * a);
     o[10] = (float)((double)gn_b[c] - mean * a);
     o[11] = (float)a;  // gamma * rstd, folded into the saved GELU gradient for the loss backward
-    if (fold_h != nullptr) {  // 16-bit taps, K padded to 16, for the tensor-core conv0 (B operand of mma.sync)
-        uint32_t* h = reinterpret_cast<uint32_t*>(fold_h + ((long long)b * CONV_DIM + c) * 16);
+    if (fold_h != nullptr) {  // 16-bit taps for the tensor-core conv0 (B operand of mma.sync), K padded to 16:
+        // halves [0, 16) = hi part, [16, 32) = lo part (tap - hi), so hi + lo carries 22 bits of each tap
+        uint32_t* h = reinterpret_cast<uint32_t*>(fold_h + ((long long)b * CONV_DIM + c) * 32);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) h[j] = pack_op((float)(w[2 * j] * a), (float)(w[2 * j + 1] * a));
+        for (int j = 0; j < 5; ++j) {
+            const float t0 = (float)(w[2 * j] * a), t1 = (float)(w[2 * j + 1] * a);
+            const uint32_t hi = pack_op(t0, t1);
+            const float2 hf = unpack_op(hi);
+            h[j] = hi;
+            h[8 + j] = pack_op(t0 - hf.x, t1 - hf.y);
+        }
         h[5] = 0u; h[6] = 0u; h[7] = 0u;
+        h[13] = 0u; h[14] = 0u; h[15] = 0u;
     }
     if (stat_out != nullptr) {
         stat_out[((long long)b * CONV_DIM + c) * 2 + 0] = (float)mean;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
                     y0 = fmaf(w0[j], xw[j], y0);
                     y1 = fmaf(w1[j], xw[j], y1);
                 }
-                packed = pack_op(gelu_erf(y0), gelu_erf(y1));
+                packed = pack_op(gelu_act(y0), gelu_act(y1));
             }
             o[(long long)t * (CONV_DIM / 2)] = packed;
         }
@@ -228,6 +236,10 @@ int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B,
 // ---------------------------------------------------------------------------------------------
 // Tensor-core conv0: the 10-tap stride-5 conv as mma.sync m16n8k16 (fp16 in, fp32 accumulate):
 //   A[t][k] = x[5 t + k] (k < 16; taps 10..15 meet zero weights),  B[k][c] = folded taps (GroupNorm folded in).
+// fp16 carries 11 bits, 16-bit PCM and trained band-pass taps need more: on real speech a plain fp16 product was
+// measured 3-80x noisier than the fp16 rounding of the output (a filter's stop-band leakage scales with the
+// quantisation of its taps and of the samples).  So samples and taps are split x = xh + xl, w = wh + wl and
+// the product is three MMAs, xh wh + xl wh + xh wl (error ~2^-22, below fp32 accumulation noise).
 // One block = 64 frames x 512 channels, warp w owns channels [64 w, 64 w + 64).  The scalar kernel above spends
 // 20 of its ~27 instructions per element on FMAs and shared loads; here the FMAs are 32 mma per warp and what
 // remains is the GELU.  Lanes of a quad trade halves so every store instruction writes full 32 B sectors.
@@ -237,7 +249,7 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
+__global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
                                                         int B, const float* __restrict__ fold,
                                                         const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
     const int row_base = blockIdx.x * C0_ROWS;
@@ -253,14 +265,16 @@ __global__ void __launch_bounds__(256) conv0_mma_kernel(const float* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, q = lane & 3;
     // B fragments + shifts of this warp's 8 channel tiles
-    uint32_t bf[8][2];
+    uint32_t bf[8][2], bl[8][2];
     float sh[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const int cb = warp * 64 + nt * 8;
-        const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cb + r) * 16);
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cb + r) * 32);
         bf[nt][0] = __ldg(h + q);
         bf[nt][1] = __ldg(h + q + 4);
+        bl[nt][0] = __ldg(h + 8 + q);
+        bl[nt][1] = __ldg(h + 8 + q + 4);
         sh[nt][0] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q) * 12 + 10);
         sh[nt][1] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q + 1) * 12 + 10);
     }
@@ -268,13 +282,17 @@ __global__ void __launch_bounds__(256) conv0_mma_kernel(const float* __restrict_
     const int valid = m.T0 - t_base;
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
-        uint32_t af[4];
+        uint32_t af[4], al[4];
         {
             const int i0 = 5 * (mt * 16 + r) + 2 * q, i1 = i0 + 40;  // rows r and r + 8
-            af[0] = pack_op(xs[i0], xs[i0 + 1]);
-            af[1] = pack_op(xs[i1], xs[i1 + 1]);
-            af[2] = pack_op(xs[i0 + 8], xs[i0 + 9]);
-            af[3] = pack_op(xs[i1 + 8], xs[i1 + 9]);
+            const int idx[4] = {i0, i1, i0 + 8, i1 + 8};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float x0 = xs[idx[k]], x1 = xs[idx[k] + 1];
+                af[k] = pack_op(x0, x1);
+                const float2 hf = unpack_op(af[k]);
+                al[k] = pack_op(x0 - hf.x, x1 - hf.y);
+            }
         }
         const int row0 = mt * 16 + r, row1 = row0 + 8;
         op_t* o0 = out + (long long)(row_base + row0) * CONV_DIM + warp * 64 + 4 * q;
@@ -283,11 +301,15 @@ __global__ void __launch_bounds__(256) conv0_mma_kernel(const float* __restrict_
         for (int np = 0; np < 4; ++np) {  // pairs of channel tiles: 16 channels = 32 B per row per quad
             float c0[4] = {sh[2 * np][0], sh[2 * np][1], sh[2 * np][0], sh[2 * np][1]};
             float c1[4] = {sh[2 * np + 1][0], sh[2 * np + 1][1], sh[2 * np + 1][0], sh[2 * np + 1][1]};
+            mma_f16_16816(c0, al, bf[2 * np][0], bf[2 * np][1]);
+            mma_f16_16816(c1, al, bf[2 * np + 1][0], bf[2 * np + 1][1]);
+            mma_f16_16816(c0, af, bl[2 * np][0], bl[2 * np][1]);
+            mma_f16_16816(c1, af, bl[2 * np + 1][0], bl[2 * np + 1][1]);
             mma_f16_16816(c0, af, bf[2 * np][0], bf[2 * np][1]);
             mma_f16_16816(c1, af, bf[2 * np + 1][0], bf[2 * np + 1][1]);
             // packed pairs: e = tile 2np (cols 2q, 2q+1), f = tile 2np+1, rows row0 / row1
-            uint32_t e0 = pack_op(gelu_erf(c0[0]), gelu_erf(c0[1])), e1 = pack_op(gelu_erf(c0[2]), gelu_erf(c0[3]));
-            uint32_t f0 = pack_op(gelu_erf(c1[0]), gelu_erf(c1[1])), f1 = pack_op(gelu_erf(c1[2]), gelu_erf(c1[3]));
+            uint32_t e0 = pack_op(gelu_act(c0[0]), gelu_act(c0[1])), e1 = pack_op(gelu_act(c0[2]), gelu_act(c0[3]));
+            uint32_t f0 = pack_op(gelu_act(c1[0]), gelu_act(c1[1])), f1 = pack_op(gelu_act(c1[2]), gelu_act(c1[3]));
             // lane q stores channels 4q..4q+3 of the 16: q<2 -> from tile 2np lanes (2q, 2q+1); q>=2 -> tile 2np+1
             const int src = (lane & ~3) | ((2 * q) & 3);
             const uint32_t a_e0 = __shfl_sync(0xffffffffu, e0, src), b_e0 = __shfl_sync(0xffffffffu, e0, src + 1);

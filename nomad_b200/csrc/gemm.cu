@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
     } else if (flags & EPI_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = gelu_act(v[j]);
     }
     if (row_ok && (flags & EPI_MUL_AUX)) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
@@ -723,7 +723,9 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
     // NOMAD_B200_EPI16 overrides (0 = never, 2 = always).
     static const int epi16 = getenv("NOMAD_B200_EPI16") ? atoi(getenv("NOMAD_B200_EPI16")) : 1;
-    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU)) != 0 && args.K <= 1024;
+    // The same holds for a short mainloop whose epilogue streams an fp32 residual in and an fp32 tile out (out-proj,
+    // K = 768: HBM-bound, 0.125 -> 0.106 ms with twice the warps keeping loads in flight).
+    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU | EPI_RESID | EPI_RESID_LN)) != 0 && args.K <= 1024;
     if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }

@@ -97,7 +97,7 @@ struct Workspace {
     uint32_t* attn_items;  // [Plan::attn_items.size()] work list of the attention kernel
     double* stat_part;   // [B][max_chunks][65]
     float* c0_fold;      // [B][512][12]: 10 folded taps, shift, gamma * rstd
-    op_t* c0_fold_h;     // [B][512][16]: the folded taps as 16-bit, K padded to 16 (tensor-core conv0)
+    op_t* c0_fold_h;     // [B][512][32]: the folded taps as 16-bit hi | lo halves, K padded to 16 (tensor-core conv0)
     float* gn_stat;      // save mode: [B][512][2] mean and rstd of the raw conv0 output per (utt, channel)
     op_t* y[7];          // conv level outputs, level l: (rows0 >> l) + 8 rows x 512
     op_t* aux[7];        // save mode: gelu'(pre-activation) per level (level 0: times gamma * rstd)

@@ -221,7 +221,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant
                                                pack_op(gr[8 * j + 4], gr[8 * j + 5]), pack_op(gr[8 * j + 6], gr[8 * j + 7]));
                     } else if (args.flags & EPI_GELU) {
 #pragma unroll
-                        for (int j = 0; j < POS_GC; ++j) v[j] = gelu_erf(v[j]);
+                        for (int j = 0; j < POS_GC; ++j) v[j] = gelu_act(v[j]);
                     }
                     uint4* op = reinterpret_cast<uint4*>(args.out + m * EMBED + g * POS_GC);
 #pragma unroll

@@ -30,6 +30,8 @@ CASES = {
     "big768": (51200, 768, 3072, 0, 0, 1, 1 | 4 | 8),
     "bigqkv": (51200, 2304, 768, 0, 0, 1, 1 | 16),
     "bigconv": (409600, 512, 1536, 1024, 0, 1, 2 | 16),
+    "bigout": (51200, 768, 768, 0, 0, 1, 1 | 4 | 8),
+    "bigconv2": (204800, 512, 1536, 1024, 0, 1, 2 | 16),
 }
 
 
@@ -107,6 +109,17 @@ def run_case(name):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         msg += f" time={ms:.3f} ms {2.0 * M * N * K * batch / ms / 1e9:.1f} TFLOP/s"
+        if not lda and batch == 1:  # cuBLAS fp16 on the same shape (no epilogue), for reference
+            a2, b2 = a_buf[0], b[0].t().contiguous()
+            for _ in range(3):
+                torch.matmul(a2, b2)
+            e0.record()
+            for _ in range(10):
+                torch.matmul(a2, b2)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 10
+            msg += f" | cuBLAS {ms2:.3f} ms {2.0 * M * N * K / ms2 / 1e9:.1f} TFLOP/s"
     print(msg, flush=True)
     tol = 0.02 * max(scale, 1.0)
     bad = [k for k, v in out.items() if not (v <= tol)]
