@@ -93,6 +93,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
         w.ln0_out = (op_t*)take(2ull * CONV_DIM * (F + 8));
     }
     w.ln_stats = (float*)take(4ull * 2 * 2 * F);  // two alternating slots
+    w.ln_part = save ? nullptr : (float*)take(sizeof(float) * 2 * 2 * LN_PARTS * F);
     w.x = (float*)take(4ull * EMBED * F);
     w.xh = (op_t*)take(2ull * EMBED * F);
     w.pos_g = (op_t*)take(2ull * POS_G * POS_GC * (p.pos_rows + POS_K));
@@ -165,6 +166,37 @@ static std::vector<op_t> transpose_op(const std::vector<op_t>& src, size_t rows,
     for (size_t r = 0; r < rows; ++r)
         for (size_t c = 0; c < cols; ++c) v[c * rows + r] = src[r * cols + c];
     return v;
+}
+
+// LayerNorm folded into the consuming Linear (EPI_LN_FOLD): W' = W diag(gamma) as op_t, s[n] = sum_k W'[n][k] of
+// the ROUNDED values (what the tensor core multiplies), c[n] = sum_k W[n][k] beta[k] + bias[n].  `scale` is applied
+// to rows [0, scaled_rows) (the q rows of the fused QKV weight carry head_dim^-0.5).
+static int upload_folded(Handle* h, const float* const* w_parts, const float* const* b_parts, int n_parts, int rows_per_part,
+                         int K, const float* gamma, const float* beta, float scale0, op_t** w_f, float** s_out,
+                         float** c_out) {
+    const int N = n_parts * rows_per_part;
+    std::vector<op_t> wf((size_t)N * K);
+    std::vector<float> sv(N), cv(N);
+    for (int part = 0; part < n_parts; ++part) {
+        const float sc = part == 0 ? scale0 : 1.0f;
+        for (int r = 0; r < rows_per_part; ++r) {
+            const float* wr = w_parts[part] + (size_t)r * K;
+            const size_t n = (size_t)part * rows_per_part + r;
+            double ssum = 0.0, csum = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const op_t q = f2op(wr[k] * sc * gamma[k]);
+                wf[n * K + k] = q;
+                ssum += (double)op2f(q);
+                csum += (double)wr[k] * sc * (double)beta[k];
+            }
+            sv[n] = (float)ssum;
+            cv[n] = (float)(csum + (double)b_parts[part][r] * sc);
+        }
+    }
+    NB_TRY(upload(h, wf, w_f));
+    NB_TRY(upload(h, sv, s_out));
+    NB_TRY(upload(h, cv, c_out));
+    return 0;
 }
 
 #define GET(var, name, numel)                         \
@@ -315,6 +347,21 @@ static int build_weights(Handle* h, TensorTable& tt) {
         NB_TRY(upload_f32(h, e1, 768, &L.ln1_b));
         NB_TRY(upload_f32(h, g2, 768, &L.ln2_g));
         NB_TRY(upload_f32(h, e2, 768, &L.ln2_b));
+        {
+            const float* wp[1] = {w1};
+            const float* bp[1] = {b1};
+            NB_TRY(upload_folded(h, wp, bp, 1, 3072, 768, g1, e1, 1.0f, &L.w_fc1_f, &L.s_fc1, &L.c_fc1));
+        }
+        L.w_qkv_f = nullptr;
+        L.s_qkv = L.c_qkv = nullptr;
+        if (l > 0) {  // this layer's QKV reads the previous layer's final_layer_norm
+            const std::string Qp = P + "encoder.layers." + std::to_string(l - 1) + ".";
+            GET(pg2, Qp + "final_layer_norm.weight", 768);
+            GET(pe2, Qp + "final_layer_norm.bias", 768);
+            const float* wp[3] = {wq, wk, wv};
+            const float* bp[3] = {bq, bk, bv};
+            NB_TRY(upload_folded(h, wp, bp, 3, 768, 768, pg2, pe2, qs, &L.w_qkv_f, &L.s_qkv, &L.c_qkv));
+        }
     }
     // --- scoring head (nomad.py:219-222): Linear(768, 256) stored transposed for coalesced GEMV
     GET(hw, "embedding_layer.1.weight", 256LL * 768);
@@ -435,14 +482,29 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
         }
         NB_TRY(launch_pos_finish_ln(st, ws.x0, ws.pos_y, ws.meta, p.B, F, w.lne_g, w.lne_b, ws.x, ws.xh));
     }
+    // Scoring path (tensor-core GEMMs, nothing saved, no per-layer outputs wanted): no LayerNorm kernel runs inside
+    // the layer stack.  A residual-adding GEMM (out-proj, FC2) stores its fp32 pre-LN rows, a 16-bit copy of them and
+    // per-row partial statistics; the next GEMM takes the un-normalised copy as its A operand and applies the
+    // LayerNorm algebraically in its epilogue (EPI_LN_FOLD); the next residual is rebuilt from the fp32 rows
+    // (EPI_RESID_LN).  Only the last layer's final_layer_norm is materialised, for the pooling kernel.
+    const bool fold_ln = impl == 0 && !save && layers_out == nullptr &&
+                         !(getenv("NOMAD_B200_LN_FOLD") && atoi(getenv("NOMAD_B200_LN_FOLD")) == 0);
     for (int l = 0; l < LAYERS; ++l) {
         const LayerWeights& L = w.layer[l];
         const LayerBufs& Lb = ws.layer[l];
         if (l == 0 || save) NB_CUDA(cudaMemsetAsync(Lb.attn, 0, 2ull * EMBED * F, st));  // padded rows stay finite
+        float* part1 = fold_ln ? ws.ln_part : nullptr;                             // statistics of pre1 (this layer)
+        float* part2 = fold_ln ? ws.ln_part + 2ll * LN_PARTS * F : nullptr;        // statistics of pre2
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
-            GemmOperand Bw{L.w_qkv, 3 * EMBED, EMBED, 0, 0};
+            GemmOperand Bw{(fold_ln && l > 0) ? L.w_qkv_f : L.w_qkv, 3 * EMBED, EMBED, 0, 0};
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_OUT_H16, L.b_qkv, nullptr, nullptr, Lb.qkv, 3 * EMBED);
+            if (fold_ln && l > 0) {  // xh holds the un-normalised pre2 of layer l - 1
+                e.flags = EPI_LN_FOLD | EPI_OUT_H16;
+                e.ln_part = part2;
+                e.fold_s = L.s_qkv;
+                e.fold_c = L.c_qkv;
+            }
             NB_TRY(gemm_h16(st, A, Bw, (int)F, 3 * EMBED, EMBED, 1, e, impl));
         }
         if (impl == 0) {
@@ -471,16 +533,28 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             } else {
                 e = epi_linear(EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32, L.b_o, ws.layer[l - 1].pre2, Lb.pre1, nullptr, EMBED);
                 e.ln_stats = st2;
+                e.ln_part = part2;
                 e.ln_g = w.layer[l - 1].ln2_g;
                 e.ln_b = w.layer[l - 1].ln2_b;
             }
+            if (fold_ln) {
+                e.flags |= EPI_OUT_H16 | EPI_STATS_OUT;
+                e.out_h = ws.xh;
+                e.part_out = part1;
+            }
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, p.B, F, L.ln1_g, L.ln1_b, nullptr, ws.xh, st1, nullptr, 0));
+        if (!fold_ln) NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, p.B, F, L.ln1_g, L.ln1_b, nullptr, ws.xh, st1, nullptr, 0));
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
-            GemmOperand Bw{L.w_fc1, FFN, EMBED, 0, 0};
+            GemmOperand Bw{fold_ln ? L.w_fc1_f : L.w_fc1, FFN, EMBED, 0, 0};
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, L.b_fc1, nullptr, nullptr, ws.ffn_h, FFN);
+            if (fold_ln) {
+                e.flags = EPI_LN_FOLD | EPI_GELU | EPI_OUT_H16;
+                e.ln_part = part1;
+                e.fold_s = L.s_fc1;
+                e.fold_c = L.c_fc1;
+            }
             if (save) {
                 e.flags |= EPI_SAVE_DGELU;
                 e.aux_out = Lb.ffn_aux;
@@ -492,13 +566,21 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             GemmOperand Bw{L.w_fc2, EMBED, FFN, 0, 0};
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32, L.b_fc2, Lb.pre1, Lb.pre2, nullptr, EMBED);
             e.ln_stats = st1;
+            e.ln_part = part1;
             e.ln_g = L.ln1_g;
             e.ln_b = L.ln1_b;
+            const bool last = l == LAYERS - 1;
+            if (fold_ln && !last) {
+                e.flags |= EPI_OUT_H16 | EPI_STATS_OUT;
+                e.out_h = ws.xh;
+                e.part_out = part2;
+            }
             NB_TRY(gemm_h16(st, A, Bw, (int)F, EMBED, FFN, 1, e, impl));
+            float* lo = layers_out ? layers_out + (size_t)l * p.B * layer_T * EMBED : nullptr;
+            if (!fold_ln || last)
+                NB_TRY(launch_ln768(st, Lb.pre2, ws.meta, p.B, F, L.ln2_g, L.ln2_b, last ? ws.x : nullptr, ws.xh, st2, lo,
+                                    layer_T));
         }
-        float* lo = layers_out ? layers_out + (size_t)l * p.B * layer_T * EMBED : nullptr;
-        const bool last = l == LAYERS - 1;
-        NB_TRY(launch_ln768(st, Lb.pre2, ws.meta, p.B, F, L.ln2_g, L.ln2_b, last ? ws.x : nullptr, ws.xh, st2, lo, layer_T));
     }
     return 0;
 }

@@ -49,8 +49,33 @@ struct GemmArgs {
 // full 32 B sectors / 128 B lines per instruction.
 // Epilogue for one warp x 32-column chunk: lane owns row `row` (v[] = its fp32 accumulators).  Executed by all
 // 32 lanes (staging is warp-collective); lanes whose row is past M skip the loads and are never flushed.
+// Per-row state an epilogue thread carries across the chunks of its tile.
+struct RowCtx {
+    float2 st;       // (mean, rstd) of the LayerNorm input row (EPI_LN_FOLD / EPI_RESID_LN)
+    float pm, pM2;   // statistics of the previous (even) 32-column chunk (EPI_STATS_OUT)
+};
+// (mean, rstd) of a 768-wide row from its LN_PARTS partial (mean, M2) pairs of 64 columns each (Chan et al.)
+__device__ __forceinline__ float2 ln_row_stats(const float* part, long long row) {
+    const float4* p = reinterpret_cast<const float4*>(part + row * (2 * LN_PARTS));
+    float m[LN_PARTS], M2 = 0.f, mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_PARTS / 2; ++i) {
+        const float4 t = __ldg(p + i);
+        m[2 * i] = t.x; m[2 * i + 1] = t.z;
+        M2 += t.y + t.w;
+        mean += t.x + t.z;
+    }
+    mean *= 1.0f / LN_PARTS;
+    float d2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_PARTS; ++i) d2 = fmaf(m[i] - mean, m[i] - mean, d2);
+    const float var = fmaf(64.0f, d2, M2) * (1.0f / (64.0f * LN_PARTS));
+    return make_float2(mean, rsqrtf(var + 1e-5f));
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
-                                               int rows_valid, int col0, int ncols, int b, float* stage, int lane) {
+                                               int rows_valid, int col0, int ncols, int b, float* stage, int lane,
+                                               RowCtx& rc) {
     const int flags = e.flags;
     const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     const long long woff = (row - lane) * e.ldo + col0 + (long long)b * e.out_bstride;  // this warp's first row
@@ -61,6 +86,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             if (j * 4 < ncols) {
                 const float4 t = __ldg(bp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+        }
+    }
+    if (row_ok && (flags & EPI_LN_FOLD)) {
+        const float4* sp = reinterpret_cast<const float4*>(e.fold_s + col0);
+        const float4* cp = reinterpret_cast<const float4*>(e.fold_c + col0);
+        const float nm = -rc.st.x, rs = rc.st.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j * 4 < ncols) {
+                const float4 a = __ldg(sp + j), c = __ldg(cp + j);
+                v[4 * j + 0] = fmaf(rs, fmaf(nm, a.x, v[4 * j + 0]), c.x);
+                v[4 * j + 1] = fmaf(rs, fmaf(nm, a.y, v[4 * j + 1]), c.y);
+                v[4 * j + 2] = fmaf(rs, fmaf(nm, a.z, v[4 * j + 2]), c.z);
+                v[4 * j + 3] = fmaf(rs, fmaf(nm, a.w, v[4 * j + 3]), c.w);
             }
         }
     }
@@ -103,7 +143,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         // residual = LayerNorm(pre-LN row) rebuilt from its saved statistics: saves the fp32 write + read of the
         // normalised residual stream (the LayerNorm kernel then only emits the 16-bit GEMM operand)
         const float4* rp = reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0);
-        const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row);
+        const float2 st = rc.st;
         const float4* gp = reinterpret_cast<const float4*>(e.ln_g + col0);
         const float4* bp = reinterpret_cast<const float4*>(e.ln_b + col0);
 #pragma unroll
@@ -115,6 +155,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
                 v[4 * j + 2] += fmaf((t.z - st.x) * st.y, g.z, bb.z);
                 v[4 * j + 3] += fmaf((t.w - st.x) * st.y, g.w, bb.w);
             }
+        }
+    }
+    if (flags & EPI_STATS_OUT) {  // two-pass statistics of this chunk, merged pairwise into 64-column partials
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s4[j & 3] += v[j];
+        const float mc = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 32.0f);
+        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) q4[j & 3] = fmaf(v[j] - mc, v[j] - mc, q4[j & 3]);
+        const float M2c = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        if ((col0 & 32) == 0) {
+            rc.pm = mc;
+            rc.pM2 = M2c;
+        } else if (row_ok) {
+            const float d = rc.pm - mc;
+            reinterpret_cast<float2*>(e.part_out)[row * LN_PARTS + (col0 >> 6)] =
+                make_float2(0.5f * (rc.pm + mc), rc.pM2 + M2c + 16.0f * d * d);
         }
     }
     if (flags & EPI_OUT_F32) {
@@ -230,6 +288,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
     double row_sum = 0.0;
+    RowCtx rc;
+    rc.st = make_float2(0.f, 1.f);
+    rc.pm = rc.pM2 = 0.f;
+    if (!CDIST && row_ok && (args.epi.flags & (EPI_LN_FOLD | EPI_RESID_LN)))
+        rc.st = args.epi.ln_part != nullptr ? ln_row_stats(args.epi.ln_part, row)
+                                             : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
 #pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
@@ -251,7 +315,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
-            else epilogue_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane);
+            else epilogue_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     if (CDIST && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
@@ -747,6 +811,11 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         NB_CHECK(!(epi.flags & EPI_RESID) || (epi.ldr % 4 == 0 && epi.resid_bstride % 4 == 0),
                  "GEMM residual leading dimension must be a multiple of 4");
     }
+    NB_CHECK(!(epi.flags & (EPI_LN_FOLD | EPI_STATS_OUT)) || impl == 0, "LayerNorm-folding epilogues exist only in the tensor-core kernel");
+    NB_CHECK(!(epi.flags & EPI_STATS_OUT) || (N == 64 * LN_PARTS && batch == 1 && epi.part_out != nullptr),
+             "EPI_STATS_OUT needs N = %d", 64 * LN_PARTS);
+    NB_CHECK(!(epi.flags & EPI_LN_FOLD) || (epi.ln_part && epi.fold_s && epi.fold_c && N % 4 == 0 && batch == 1),
+             "EPI_LN_FOLD needs partial statistics, s and c vectors");
     if (impl == 1) {
         dim3 grid((N + 15) / 16, (M + 15) / 16, batch), block(16, 16);
         gemm_simt_kernel<<<grid, block, 0, st>>>(A, B, args);
@@ -767,7 +836,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
             const double used = (double)N / (((N + bn - 1) / bn) * (double)bn);
             return tile_eff * used * tiles / (std::ceil(tiles / sms) * sms);
         };
-        const bool use192 = force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0);
+        const bool use192 = (epi.flags & EPI_STATS_OUT) ? false : (force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0));
         if (use192) {
             args.umma_n = 192;
             return launch_tc<192>(st, A, B, args);

@@ -15,6 +15,13 @@ enum : int {
     EPI_MUL_AUX = 32,  // * aux[row, col] (op_t)  -- dgrad through GELU: aux holds gelu'(pre-activation)
     EPI_CDIST = 64,
     EPI_RESID_LN = 256,  // + LayerNorm(resid row) recomputed from saved (mean, rstd): (r - mean) * rstd * g + b
+    // LayerNorm of the A operand folded into this GEMM: A holds the UN-normalised rows x, the weights carry gamma
+    // (W' = W diag(gamma)), and out = rstd_r * (acc - mean_r * s[col]) + c[col] with s = row sums of W' and
+    // c = W beta + bias -- exact algebra, so no LayerNorm kernel has to run between the two GEMMs.
+    EPI_LN_FOLD = 512,
+    // also emit per-row partial LayerNorm statistics of the fp32 output, one (mean, M2) pair per 64 columns, for
+    // a later EPI_LN_FOLD / EPI_RESID_LN consumer (needs N % 256 == 0)
+    EPI_STATS_OUT = 1024,
     EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
 };
 
@@ -40,7 +47,11 @@ struct GemmEpilogue {
     const float* resid;       // fp32, element (row, col) at resid[row * ldr + col + b * resid_bstride]
     long long ldr;
     long long resid_bstride;
-    const float* ln_stats;    // EPI_RESID_LN: [rows][2] = mean, rstd of the resid row
+    const float* ln_stats;    // EPI_RESID_LN: [rows][2] = mean, rstd of the resid row (when ln_part is null)
+    const float* ln_part;     // EPI_RESID_LN / EPI_LN_FOLD: [rows][LN_PARTS][2] partial (mean, M2) per 64 columns
+    float* part_out;          // EPI_STATS_OUT target, same layout
+    const float* fold_s;      // EPI_LN_FOLD: [N] row sums of the gamma-folded (rounded) weights
+    const float* fold_c;      // EPI_LN_FOLD: [N] W beta + bias
     const float* ln_g;        // [N]
     const float* ln_b;        // [N]
     const op_t* aux;          // 16-bit, same indexing as out (ldo / out_bstride)
@@ -59,6 +70,8 @@ struct GemmEpilogue {
 };
 
 // C[b] = epilogue(A[b] (M x K) * B[b]^T (N x K)).  impl: 0 = tcgen05/TMA kernel, 1 = SIMT check kernel.
+static constexpr int LN_PARTS = 12;  // 768 / 64
+
 int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl);
 

@@ -39,6 +39,11 @@ struct LayerWeights {
     op_t *w_qkv, *w_o, *w_fc1, *w_fc2;          // [N][K] K-major op_t
     float *b_qkv, *b_o, *b_fc1, *b_fc2;
     float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    // LayerNorm folded into the consuming GEMM (scoring path, EPI_LN_FOLD): weights times the gamma of the
+    // LayerNorm that feeds them (QKV: previous layer's final_layer_norm, null for layer 0; FC1: this layer's
+    // self_attn_layer_norm), s = row sums of the rounded folded weights, c = W beta + bias
+    op_t *w_qkv_f, *w_fc1_f;
+    float *s_qkv, *c_qkv, *s_fc1, *c_fc1;
     // transposed copies for the dgrad GEMMs of the loss path
     op_t *wt_qkv, *wt_o, *wt_fc1, *wt_fc2;      // [K][N] -> used as [N'=K][K'=N]
 };
@@ -107,6 +112,7 @@ struct Workspace {
     op_t* pos_y;         // [pos_rows][768] GELU(pos conv)
     op_t* pos_aux;       // save mode: gelu' of the pos conv pre-activation, [pos_rows][768]
     float* ln_stats;     // frames x 2: (mean, rstd) of the most recent LayerNorm(768) input rows
+    float* ln_part;      // 2 x frames x LN_PARTS x 2: partial (mean, M2) of the pre-LN rows (scoring path)
     float* x;            // residual stream, frames x 768 fp32
     op_t* xh;            // 16-bit copy (GEMM operand)
     op_t* ffn_h;         // frames x 3072
