@@ -73,6 +73,14 @@ __device__ __forceinline__ float2 ln_row_stats(const float* part, long long row)
     return make_float2(mean, rsqrtf(var + 1e-5f));
 }
 
+// (mean, rstd) of this thread's row for EPI_LN_FOLD / EPI_RESID_LN.  Called BEFORE the wait for the accumulator so
+// the (L2-latency) loads overlap the mainloop of the tile instead of sitting at the head of its epilogue.
+__device__ __forceinline__ float2 epilogue_row_stats(const GemmArgs& args, long long row) {
+    if (row >= args.M || !(args.epi.flags & (EPI_LN_FOLD | EPI_RESID_LN))) return make_float2(0.f, 1.f);
+    return args.epi.ln_part != nullptr ? ln_row_stats(args.epi.ln_part, row)
+                                       : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
@@ -227,12 +235,31 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& e, float v, 
 // near-duplicate rows, so squared distances below CD_REFINE are re-evaluated with fp32 direct differences
 // (rare); above it the fp32 Gram error (~2e-7 on d^2) keeps d within 3e-6 of scipy's float64 result.
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;  // MUFU.SQRT: relative error ~2^-22, i.e. < 5e-7 on distances <= 2 (the 1e-5 bound has room for it)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// exact fp32 re-evaluation of one squared distance (direct differences)
+__device__ __noinline__ float cdist_exact_d2(const float* __restrict__ a, const float* __restrict__ b) {
+    const float4* pa = reinterpret_cast<const float4*>(a);
+    const float4* pb = reinterpret_cast<const float4*>(b);
+    float s = 0.f;
+    for (int k = 0; k < 64; ++k) {
+        const float4 x = __ldg(pa + k), y = __ldg(pb + k);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d3 = x.z - y.z, d4 = x.w - y.w;
+        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d3, d3, s); s = fmaf(d4, d4, s);
+    }
+    return s;
+}
+
 __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                               int rows_valid, int col0, int ncols, float* stage, int lane) {
     const float na = row_ok ? __ldg(e.norm_a + row) : 0.f;
     float s32 = 0.f;  // 32 distances <= 2 each: an fp32 partial sum is exact to ~1e-7; fp64 only across chunks
+    const bool full = ncols == 32;  // warp-uniform
     float nbv[32];
-    if (ncols == 32) {
+    if (full) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(e.norm_b + col0) + j);  // col0 % 32 == 0
@@ -242,30 +269,31 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 #pragma unroll
         for (int j = 0; j < 32; ++j) nbv[j] = j < ncols ? __ldg(e.norm_b + col0 + j) : 0.f;
     }
+    // squared distances of the whole chunk first; ONE test decides whether any of them needs the exact path
+    const float m2s = -2.0f * e.cd_inv_scale;
+    float dmin = CD_REFINE;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        if (row_ok && j < ncols) {
-            float d2 = na + nbv[j] - 2.0f * (v[j] * e.cd_inv_scale);
-            if (d2 < CD_REFINE) {
-                const float4* pa = reinterpret_cast<const float4*>(e.cd_a + row * 256);
-                const float4* pb = reinterpret_cast<const float4*>(e.cd_b + (long long)(col0 + j) * 256);
-                float s = 0.f;
-                for (int k = 0; k < 64; ++k) {
-                    const float4 x = __ldg(pa + k), y = __ldg(pb + k);
-                    const float d0 = x.x - y.x, d1 = x.y - y.y, d3 = x.z - y.z, d4 = x.w - y.w;
-                    s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d3, d3, s); s = fmaf(d4, d4, s);
-                }
-                d2 = s;
-            }
-            v[j] = sqrtf(fmaxf(d2, 0.f));
-            s32 += v[j];
-        }
+        v[j] = fmaf(v[j], m2s, na + nbv[j]);
+        if (full || j < ncols) dmin = fminf(dmin, v[j]);
     }
-    const double rs = (double)s32;
+    if (row_ok && dmin < CD_REFINE) {  // rare: near-duplicate rows
+#pragma unroll
+        for (int j = 0; j < 32; ++j)  // static indices keep v[] in registers
+            if (j < ncols && v[j] < CD_REFINE) v[j] = cdist_exact_d2(e.cd_a + row * 256, e.cd_b + (long long)(col0 + j) * 256);
+    }
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        v[j] = sqrt_approx(fmaxf(v[j], 0.f));
+        if (full || j < ncols) s4[j & 3] += v[j];
+    }
+    s32 = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    const double rs = row_ok ? (double)s32 : 0.0;
     if (e.out_f != nullptr) {  // warp-uniform
         stage_put_f32(stage, v, lane);
         float* wout = e.out_f + (row - lane) * e.ldo + col0;
-        if (ncols == 32 && (e.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(wout) & 15) == 0)) {
+        if (full && (e.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(wout) & 15) == 0)) {
             stage_flush_f32(stage, wout, e.ldo, rows_valid, ncols, lane);
         } else {  // ragged / unaligned: one row per instruction, lane = column (still full-line coalesced)
             __syncwarp();
@@ -283,17 +311,15 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
 template <int CHUNKS, bool PAIR, bool CDIST>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
-                                              int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage) {
+                                              int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
+                                              float2 row_st) {
     const bool row_ok = row < args.M;
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
     double row_sum = 0.0;
     RowCtx rc;
-    rc.st = make_float2(0.f, 1.f);
+    rc.st = row_st;
     rc.pm = rc.pM2 = 0.f;
-    if (!CDIST && row_ok && (args.epi.flags & (EPI_LN_FOLD | EPI_RESID_LN)))
-        rc.st = args.epi.ln_part != nullptr ? ln_row_stats(args.epi.ln_part, row)
-                                             : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
 #pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
@@ -436,11 +462,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int b = tile / (args.n_tiles * args.m_tiles);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const long long row = (long long)m_blk * BM + q * 32 + lane;
+            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const long long row = (long long)m_blk * BM + q * 32 + lane;
             epilogue_tile<CHUNKS, false, CDIST>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
-                                         row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
+                                         row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
+                                         row_st);
         }
     }
     tc_fence_before();
@@ -579,11 +607,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int b = tile / (args.n_tiles * args.m_tiles);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
+            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
             epilogue_tile<HALF / 32, true, CDIST>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
-                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024);
+                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
+                                           row_st);
         }
     }
     tc_fence_before();
@@ -782,7 +812,7 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     return 0;
 }
 static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
-    if (args.epi.flags & EPI_CDIST) return launch_pair_impl<8, true>(st, A, B, args);
+    if (args.epi.flags & EPI_CDIST) return launch_pair_impl<16, true>(st, A, B, args);  // epilogue-bound (sqrt, sums, 4 B/pair out)
     // 16 epilogue warps hide the latency of a math-heavy (GELU) epilogue when the mainloop is short (FC1, K = 768:
     // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
     // NOMAD_B200_EPI16 overrides (0 = never, 2 = always).
