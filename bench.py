@@ -39,10 +39,12 @@ CLIP_SECONDS = 4
 SR = 16000
 WORKLOAD = "configs[1]: batch embedding, 256 x 4 s synthetic 16 kHz clips, wav2vec2-base + NOMAD head"
 CPU_SAMPLE_CLIPS = 16
+PAIR_N, PAIR_M = 100_000, 1_000
 FALLBACK_PEAK_TFLOPS = 1400.0  # B200_PROFILING.md: sustained ~1.4 PFLOP/s (burst fallback 1590)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_tc_kernel<256>, ncu --set full
-# (profiles/); None until a capture exists for the current kernel.
-GEMM_DRAM_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum per tensor-core GEMM launch, averaged over the 55 GEMM launches of one
+# step (ncu, profiles/r01_gemm_dram_v6.csv: 30.9 GB per step; the algorithmic operand + result bytes of those
+# launches are 32.8 GB)
+GEMM_DRAM_TRAFFIC_BYTES = 561.9e6
 
 
 def log(*a):
@@ -212,6 +214,15 @@ def run_ours(args):
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_int64()
     lib.nomad_b200_profile_gemm_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
     lib.nomad_b200_profile_gemm(0)
+    # second named quantity of BASELINE.json's metric: pairwise distances per second (config 4 shape per GPU:
+    # 100 k degraded x 1 k NMR embeddings resident in HBM, matrix materialised + fp64 row means)
+    gq = torch.Generator().manual_seed(100 + rank)
+    deg_e = torch.nn.functional.normalize(torch.randn(PAIR_N, 256, generator=gq), dim=1).to(dev)
+    nmr_e = torch.nn.functional.normalize(torch.randn(PAIR_M, 256, generator=gq), dim=1).to(dev)
+    for _ in range(3):
+        eng.cdist_mean(deg_e, nmr_e)
+    pair_ms = timed(lambda: eng.cdist_mean(deg_e, nmr_e), 20) / 20
+    pair_mean_ms = timed(lambda: eng.cdist_mean(deg_e, nmr_e, want_matrix=False), 20) / 20
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -254,12 +265,17 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(CLIPS * 256 * 4), "api": "nomad_b200_embed_host (pinned host buffers)"},
         "gpu_launches": int(launches),
         "step_tflops": step_flops * world / (ms_per_step / 1e3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all BN variants)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_pair_kernel (tcgen05 cta_group::2, all 55 GEMM launches of the step)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": GEMM_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
                      "launches_timed": int(g_n.value), "kernel_ms_per_step": g_ms.value / args.steps,
                      "kernel_share_of_step": g_ms.value / prof_ms,
                      "profiled_ms_per_step": prof_ms / args.steps},
+        "pairwise": {"metric": "pairwise distances per second", "n": PAIR_N, "m": PAIR_M, "n_gpus": world,
+                     "value": PAIR_N * PAIR_M * world / (pair_ms / 1e3), "unit": "pairs/s",
+                     "write_GBps_per_gpu": PAIR_N * PAIR_M * 4 / (pair_ms / 1e3) / 1e9,
+                     "means_only_value": PAIR_N * PAIR_M * world / (pair_mean_ms / 1e3),
+                     "roof": "3-pass split-fp16 Gram: 1536 FLOP/pair on the tensor roof, 4 B/pair written on the HBM roof"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

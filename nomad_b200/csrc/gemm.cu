@@ -37,8 +37,14 @@ struct GemmArgs {
     int umma_n;  // N of the MMA instruction (<= BN, multiple of 16)
     int m_tiles, n_tiles;
     int a_wrap;  // GemmOperand::k_wrap of A
+    unsigned sleep_ns;  // back-off of the waiting TMA / MMA role threads (0 = spin); they share schedulers with epilogue warps
     GemmEpilogue epi;
 };
+__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity))
+        if (ns) __nanosleep(ns);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Staged, coalesced global stores.  TMEM hands every lane one ROW of the tile, so a direct store instruction
@@ -81,29 +87,31 @@ __device__ __forceinline__ float2 epilogue_row_stats(const GemmArgs& args, long 
                                        : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
 }
 
+// FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
+template <bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
     const int flags = e.flags;
     const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     const long long woff = (row - lane) * e.ldo + col0 + (long long)b * e.out_bstride;  // this warp's first row
-    if (row_ok && (flags & EPI_BIAS)) {
+    if ((FULL || row_ok) && (flags & EPI_BIAS)) {
         const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bstride + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (j * 4 < ncols) {
+            if (FULL || j * 4 < ncols) {
                 const float4 t = __ldg(bp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
         }
     }
-    if (row_ok && (flags & EPI_LN_FOLD)) {
+    if ((FULL || row_ok) && (flags & EPI_LN_FOLD)) {
         const float4* sp = reinterpret_cast<const float4*>(e.fold_s + col0);
         const float4* cp = reinterpret_cast<const float4*>(e.fold_c + col0);
         const float nm = -rc.st.x, rs = rc.st.y;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (j * 4 < ncols) {
+            if (FULL || j * 4 < ncols) {
                 const float4 a = __ldg(sp + j), c = __ldg(cp + j);
                 v[4 * j + 0] = fmaf(rs, fmaf(nm, a.x, v[4 * j + 0]), c.x);
                 v[4 * j + 1] = fmaf(rs, fmaf(nm, a.y, v[4 * j + 1]), c.y);
@@ -122,11 +130,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_act(v[j]);
     }
-    if (row_ok && (flags & EPI_MUL_AUX)) {
+    if ((FULL || row_ok) && (flags & EPI_MUL_AUX)) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j * 8 < ncols) {
+            if (FULL || j * 8 < ncols) {
                 const uint4 t = __ldg(ap + j);
                 float2 f;
                 f = unpack_op(t.x); v[8 * j + 0] *= f.x; v[8 * j + 1] *= f.y;
@@ -136,18 +144,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    if (row_ok && (flags & EPI_RESID)) {
+    if ((FULL || row_ok) && (flags & EPI_RESID)) {
         const float4* rp =
             reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0 + (long long)b * e.resid_bstride);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (j * 4 < ncols) {
+            if (FULL || j * 4 < ncols) {
                 const float4 t = __ldg(rp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
         }
     }
-    if (row_ok && (flags & EPI_RESID_LN)) {
+    if ((FULL || row_ok) && (flags & EPI_RESID_LN)) {
         // residual = LayerNorm(pre-LN row) rebuilt from its saved statistics: saves the fp32 write + read of the
         // normalised residual stream (the LayerNorm kernel then only emits the 16-bit GEMM operand)
         const float4* rp = reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0);
@@ -156,7 +164,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         const float4* bp = reinterpret_cast<const float4*>(e.ln_b + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (j * 4 < ncols) {
+            if (FULL || j * 4 < ncols) {
                 const float4 t = __ldg(rp + j), g = __ldg(gp + j), bb = __ldg(bp + j);
                 v[4 * j + 0] += fmaf((t.x - st.x) * st.y, g.x, bb.x);
                 v[4 * j + 1] += fmaf((t.y - st.x) * st.y, g.y, bb.y);
@@ -177,7 +185,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         if ((col0 & 32) == 0) {
             rc.pm = mc;
             rc.pM2 = M2c;
-        } else if (row_ok) {
+        } else if (FULL || row_ok) {
             const float d = rc.pm - mc;
             reinterpret_cast<float2*>(e.part_out)[row * LN_PARTS + (col0 >> 6)] =
                 make_float2(0.5f * (rc.pm + mc), rc.pM2 + M2c + 16.0f * d * d);
@@ -341,7 +349,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
-            else epilogue_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
+            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
+            else epilogue_chunk<false>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     if (CDIST && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
@@ -402,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m_blk = (tile / args.n_tiles) % args.m_tiles;
                 const int b = tile / (args.n_tiles * args.m_tiles);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_role(&empty_bar[stage], phase ^ 1, args.sleep_ns);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -427,11 +436,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                mbar_wait_role(&tmem_empty[as], aphase ^ 1, args.sleep_ns);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_role(&full_bar[stage], phase, args.sleep_ns);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + Cfg::A_BYTES;
@@ -553,7 +562,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int row0 = m_blk * 256 + (int)rank * BM;
                 const int col0 = n_blk * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_role(&empty_bar[stage], phase ^ 1, args.sleep_ns);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -577,11 +586,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                mbar_wait_role(&tmem_empty[as], aphase ^ 1, args.sleep_ns);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_role(&full_bar[stage], phase, args.sleep_ns);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc_sw128(sa);
@@ -817,9 +826,13 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
     // NOMAD_B200_EPI16 overrides (0 = never, 2 = always).
     static const int epi16 = getenv("NOMAD_B200_EPI16") ? atoi(getenv("NOMAD_B200_EPI16")) : 1;
-    // The same holds for a short mainloop whose epilogue streams an fp32 residual in and an fp32 tile out (out-proj,
-    // K = 768: HBM-bound, 0.125 -> 0.106 ms with twice the warps keeping loads in flight).
-    const bool heavy = (args.epi.flags & (EPI_GELU | EPI_SAVE_DGELU | EPI_RESID | EPI_RESID_LN)) != 0 && args.K <= 1024;
+    // A short mainloop whose epilogue streams an fp32 residual in and an fp32 tile out (out-proj, K = 768) also gains
+    // from twice the warps keeping loads in flight (0.125 -> 0.106 ms) -- unless it additionally emits the 16-bit
+    // copy and the LayerNorm statistics: that epilogue does not fit the 96-register budget of the 640-thread CTA
+    // (in-model 231 us with 16 warps, 170 us with 8).
+    const int fl = args.epi.flags;
+    const bool heavy = args.K <= 1024 && ((fl & (EPI_GELU | EPI_SAVE_DGELU)) != 0 ||
+                                          ((fl & (EPI_RESID | EPI_RESID_LN)) != 0 && !(fl & EPI_STATS_OUT)));
     if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
@@ -833,6 +846,8 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
     args.epi = epi;
     args.umma_n = 0; args.m_tiles = args.n_tiles = 0;
     args.a_wrap = A.k_wrap;
+    static const unsigned sleep_ns = getenv("NOMAD_B200_GEMM_SLEEP") ? (unsigned)atoi(getenv("NOMAD_B200_GEMM_SLEEP")) : 0u;
+    args.sleep_ns = sleep_ns;
     NB_CHECK(B.k_wrap == 0, "only the A operand may use wrapped K");
     if (!(epi.flags & EPI_CDIST)) {
         NB_CHECK(N % 8 == 0 && epi.ldo % 8 == 0 && epi.out_bstride % 8 == 0,

@@ -195,6 +195,48 @@ def test_model_call_signature_matches_reference(state_dict, golden_dir):
     assert len(feats) == 13 and feats[0].shape == (3, 12, 768) and feats[12].shape == (3, 256)
 
 
+# ------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("lengths", [
+    [1, 2, 63, 64, 65, 127, 128, 129, 199, 256, 257, 511],   # every key-tile / query-tile edge
+    [999, 1500],                                              # 20 s and 30 s utterances (many tiles)
+    [99] * 64,                                                # the loss shape (config 3)
+])
+def test_attention_core_any_length(lengths):
+    """softmax(Q K^T) V per (utterance, head) through the C ABI against torch fp32, with the log-sum-exp the loss
+    backward consumes.  Scores have a wide range so the running-max rescale of the online softmax is exercised.
+    Tolerance: P and the output are 16-bit (|out| ~ 1.5 here): 4e-3 absolute; lse 1e-4."""
+    from nomad_b200 import _lib
+    lib = _lib.load()
+    T = np.asarray(lengths, dtype=np.int32)
+    frame0 = np.zeros(len(T), dtype=np.int32)
+    f = 0
+    for u, t in enumerate(T):
+        frame0[u] = f
+        f += int(t) + 3  # padding rows between utterances
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(f, 2304, generator=g) * 1.5
+    qkv[:, :768] *= 0.375
+    qkv = qkv.to(torch.float16).cuda()
+    out = torch.zeros(f, 768, dtype=torch.float16, device="cuda")
+    lse = torch.zeros(f, 12, dtype=torch.float32, device="cuda")
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    wsb = lib.nomad_b200_attention_workspace_bytes(ip(T), len(T))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.nomad_b200_attention_f16(qkv.data_ptr(), f, ip(frame0), ip(T), len(T), out.data_ptr(), lse.data_ptr(),
+                                            ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "attention")
+    torch.cuda.synchronize()
+    for u, t in enumerate(T):
+        t, f0 = int(t), int(frame0[u])
+        x = qkv[f0:f0 + t].float().view(t, 3, 12, 64)
+        q, k, v = (x[:, i].transpose(0, 1) for i in range(3))
+        s = q @ k.transpose(1, 2)
+        ref = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(t, 768)
+        assert float((out[f0:f0 + t].float() - ref).abs().max()) <= 4e-3, (u, t)
+        assert float((lse[f0:f0 + t] - torch.logsumexp(s, -1).transpose(0, 1)).abs().max()) <= 1e-4, (u, t)
+        # rows between utterances are never written
+        assert float(out[f0 + t:f0 + t + 3].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------ cdist
 def test_cdist_golden_and_properties(engine, golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_cdist.npz"))

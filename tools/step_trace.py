@@ -37,3 +37,21 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
 gaps = [evs[i+1].time_range.start - evs[i].time_range.end for i in range(len(evs)-1)]
 gaps = [g for g in gaps if g < 1000]
 print(f"median gap {np.median(gaps):.2f} us, mean {np.mean(gaps):.2f} us, sum/step {sum(gaps)/3/1e3:.2f} ms")
+# per-launch GEMM durations of the last profiled step, labelled by their position in the launch sequence
+gem = [e for e in evs if "gemm_tc" in e.name]
+per = len(gem) // 3
+last = gem[-per:]
+labels = ["conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "proj"] + [f"{n}.{l}" for l in range(12) for n in ("qkv", "out", "fc1", "fc2")]
+FL = {"conv1": 2 * 256 * 6400 * 512 * 1536, "conv2": 2 * 256 * 3200 * 512 * 1536, "conv3": 2 * 256 * 1600 * 512 * 1536,
+      "conv4": 2 * 256 * 800 * 512 * 1536, "conv5": 2 * 256 * 400 * 512 * 1024, "conv6": 2 * 256 * 200 * 512 * 1024,
+      "proj": 2 * 51200 * 768 * 512, "qkv": 2 * 51200 * 2304 * 768, "out": 2 * 51200 * 768 * 768,
+      "fc1": 2 * 51200 * 3072 * 768, "fc2": 2 * 51200 * 768 * 3072}
+if len(last) == len(labels):
+    agg2 = collections.OrderedDict()
+    for lab, e in zip(labels, last):
+        k = lab.split(".")[0]
+        d = (e.time_range.end - e.time_range.start)
+        agg2.setdefault(k, []).append(d)
+    for k, v in agg2.items():
+        us = float(np.mean(v))
+        print(f"  gemm {k:6s} n={len(v):2d}  {us:8.1f} us/launch  {FL[k] / us / 1e6:7.1f} TFLOP/s")
