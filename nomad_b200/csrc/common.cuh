@@ -209,6 +209,11 @@ __device__ __forceinline__ void stage_flush_h16(const op_t* stage, op_t* out, lo
     __syncwarp();
 }
 
+// L2 prefetch of `bytes` (multiple of 16) contiguous global bytes: no registers, no completion to wait for
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -274,12 +279,14 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// arrive on the same-named mbarrier of CTA `rank` of this cluster
+// arrive on the same-named mbarrier of CTA `rank` of this cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive does: the waiter only needs the tcgen05-fenced TMEM reads ordered, and a
+// cluster-scope release made lane 0 wait for every global store of its epilogue to drain (ncu: membar stalls).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
         "r"(rank)
         : "memory");
 }

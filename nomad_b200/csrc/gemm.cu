@@ -618,6 +618,16 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t aphase = (it >> 1) & 1;
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
             const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
+            if (!CDIST && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
+                // pull the NEXT tile's slice of the fp32 residual stream into L2 now, a whole mainloop ahead of
+                // its use: the epilogue's row loads then pay L2 latency instead of HBM latency
+                const int nt = tile + num_pairs;
+                const int n2 = nt % args.n_tiles, m2 = (nt / args.n_tiles) % args.m_tiles;
+                const long long r2 = (long long)m2 * 256 + rank * BM + q * 32 + lane;
+                const int c2 = n2 * BN + h * HALF;
+                if (r2 < args.M && c2 + HALF <= args.N)
+                    prefetch_l2_bulk(args.epi.resid + r2 * args.epi.ldr + c2, HALF * 4);
+            }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             epilogue_tile<HALF / 32, true, CDIST>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
