@@ -428,28 +428,51 @@ GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float*
 
 // wav (device, packed) -> residual stream after the 12th layer (ws.x), optionally the 12 layer outputs.
 int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st,
-                    float* layers_out, int layer_T) {
+                    float* layers_out, int layer_T, const FrontPipe* pipe) {
     const Weights& w = h->w;
     const int impl = h->gemm_impl;
     const long long F = p.frames;
     const bool save = ws.save;
-    // conv0 + GroupNorm + GELU
-    NB_TRY(launch_wave_stats(st, wav, ws.meta, p.B, p.max_chunks, ws.stat_part));
-    NB_TRY(launch_gn_fold(st, ws.stat_part, ws.meta, p.B, p.max_chunks, w.conv0_w, w.gn_g, w.gn_b, ws.c0_fold,
-                          ws.gn_stat, ws.c0_fold_h));
-    NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, p.rows0, ws.c0_fold, impl == 0 ? ws.c0_fold_h : nullptr, ws.y[0],
-                              ws.aux[0]));
-    // conv 1..6 as overlapping-row GEMMs over the flat channels-last activation
-    for (int l = 1; l < 7; ++l) {
-        const long long M = p.rows0 >> l;
-        GemmOperand A{ws.y[l - 1], M, 2 * CONV_DIM, 0, 0};
+    // The rows just past a level's last utterance are read by the next conv (its last padding output rows): keep
+    // them finite.  (Padding rows never mix with valid rows, but a NaN there would survive as 0 * NaN in P V.)
+    for (int l = 0; l < 6; ++l)
+        NB_CUDA(cudaMemsetAsync(ws.y[l] + (p.rows0 >> l) * CONV_DIM, 0, 2ull * CONV_DIM * 8, st));
+    // conv0 + GroupNorm + GELU, then conv1, per utterance group (one group unless the caller pipelines the H2D copy);
+    // conv0 of group g + 1 is issued before conv1 of group g because conv1's padding rows read one row ahead
+    FrontPipe whole;
+    whole.n_groups = 1;
+    whole.first[0] = 0;
+    whole.first[1] = p.B;
+    const FrontPipe& fp = (pipe != nullptr && pipe->n_groups > 0) ? *pipe : whole;
+    auto row_of = [&](int b) { return b < p.B ? (long long)p.utt[b].row0 : p.rows0; };
+    auto conv_level = [&](int l, long long r0, long long r1) -> int {  // level-l rows of the level-0 row range [r0, r1)
+        const long long M = (r1 - r0) >> l;
+        if (M <= 0) return 0;
+        GemmOperand A{ws.y[l - 1] + (r0 >> (l - 1)) * CONV_DIM, M, 2 * CONV_DIM, 0, 0};
         GemmOperand Bw{w.conv_w[l], CONV_DIM, (long long)CONV_KERNEL[l] * CONV_DIM, 0, 0};
-        GemmEpilogue e = epi_linear(EPI_GELU | EPI_OUT_H16, nullptr, nullptr, nullptr, ws.y[l], CONV_DIM);
+        GemmEpilogue e = epi_linear(EPI_GELU | EPI_OUT_H16, nullptr, nullptr, nullptr, ws.y[l] + (r0 >> l) * CONV_DIM, CONV_DIM);
         if (save) {
             e.flags |= EPI_SAVE_DGELU;
-            e.aux_out = ws.aux[l];
+            e.aux_out = ws.aux[l] + (r0 >> l) * CONV_DIM;
         }
-        NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, CONV_KERNEL[l] * CONV_DIM, 1, e, impl));
+        return gemm_h16(st, A, Bw, (int)M, CONV_DIM, CONV_KERNEL[l] * CONV_DIM, 1, e, impl);
+    };
+    for (int g = 0; g <= fp.n_groups; ++g) {
+        if (g < fp.n_groups) {
+            const int b0 = fp.first[g], nb = fp.first[g + 1] - fp.first[g];
+            if (pipe != nullptr && pipe->n_groups > 0) NB_CUDA(cudaStreamWaitEvent(st, fp.copied[g], 0));
+            NB_TRY(launch_wave_stats(st, wav, ws.meta, b0, nb, p.max_chunks, ws.stat_part));
+            NB_TRY(launch_gn_fold(st, ws.stat_part, ws.meta, b0, nb, p.max_chunks, w.conv0_w, w.gn_g, w.gn_b, ws.c0_fold,
+                                  ws.gn_stat, ws.c0_fold_h));
+            NB_TRY(launch_conv0_apply(st, wav, ws.meta, p.B, row_of(b0), row_of(b0 + nb), ws.c0_fold,
+                                      impl == 0 ? ws.c0_fold_h : nullptr, ws.y[0], ws.aux[0]));
+        }
+        if (g > 0) NB_TRY(conv_level(1, row_of(fp.first[g - 1]), row_of(fp.first[g])));
+    }
+    if (save) NB_TRY(launch_zero_pad_rows(st, ws.aux[1], ws.meta, p.B, 1));
+    // conv 2..6 as overlapping-row GEMMs over the flat channels-last activation
+    for (int l = 2; l < 7; ++l) {
+        NB_TRY(conv_level(l, 0, p.rows0));
         if (save) NB_TRY(launch_zero_pad_rows(st, ws.aux[l], ws.meta, p.B, l));
     }
     // LayerNorm(512) -> projection -> x0
@@ -629,6 +652,11 @@ int nomad_b200_destroy(nomad_b200_handle* hh) {
     cudaDeviceSynchronize();
     for (void* p : hh->h.allocs) cudaFree(p);
     if (hh->h.meta_host) cudaFreeHost(hh->h.meta_host);
+    if (hh->h.copy_stream) {
+        cudaStreamDestroy(hh->h.copy_stream);
+        cudaEventDestroy(hh->h.fork_event);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(hh->h.copied[i]);
+    }
     if (hh->h.meta_event) {
         cudaEvent_t* ev = (cudaEvent_t*)(void*)hh->h.meta_event;
         for (int i = 0; i < META_SLOTS; ++i) cudaEventDestroy(ev[i]);
@@ -672,8 +700,13 @@ size_t nomad_b200_embed_workspace_bytes(const int64_t* sample_offsets, int B) {
     return carve_workspace(p, nullptr, nullptr, false);
 }
 
-int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
-                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+// `pipe`: the caller stages the waveform in groups on a side stream (see FrontPipe); `issue_copies` is called right
+// after the small metadata uploads, so that those do not queue behind the bulk copies on the H2D copy engine.
+template <typename F>
+static int embed_impl(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream, const FrontPipe* pipe, F issue_copies) {
     NB_TRY(check_handle(hh));
     Handle* h = &hh->h;
     NB_CHECK(wav_dev && emb_dev && workspace_dev, "embed: null pointer");
@@ -688,9 +721,18 @@ int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t*
     NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "embed: workspace must be 1024-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     NB_TRY(upload_meta(h, p, ws, st));
-    NB_TRY(forward_encoder(h, p, ws, wav_dev, st, nullptr, 0));
+    NB_TRY(issue_copies());
+    NB_TRY(forward_encoder(h, p, ws, wav_dev, st, nullptr, 0, pipe));
     NB_TRY(launch_pool_head(st, ws.x, ws.meta, p.B, h->w.head_wt, h->w.head_b, emb_dev, nullptr));
     return 0;
+}
+
+extern "C" {
+
+int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, workspace_bytes, stream, nullptr,
+                      [] { return 0; });
 }
 
 int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const int64_t* sample_offsets, int B,
@@ -711,8 +753,42 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
              workspace_bytes, core + wav_bytes + emb_bytes);
     float* wav_dev = (float*)((char*)workspace_dev + core);
     float* emb_dev = (float*)((char*)workspace_dev + core + wav_bytes);
-    NB_CUDA(cudaMemcpyAsync(wav_dev, wav_host + sample_offsets[0], (size_t)total * 4, cudaMemcpyHostToDevice, st));
-    NB_TRY(nomad_b200_embed(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, core, stream));
+    // H2D in up to 4 utterance groups of about equal size on a side stream; the compute stream picks each group up
+    // as it lands (front end of group g overlaps the copy of group g + 1)
+    static const int max_groups = getenv("NOMAD_B200_H2D_GROUPS") ? atoi(getenv("NOMAD_B200_H2D_GROUPS")) : 4;
+    FrontPipe pipe;
+    if (!h->copy_stream) {
+        NB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        NB_CUDA(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) NB_CUDA(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
+    }
+    {
+        int G = max_groups < 1 ? 1 : (max_groups > 8 ? 8 : max_groups);
+        if (G > B) G = B;
+        pipe.n_groups = G;
+        pipe.first[0] = 0;
+        int b = 0;
+        for (int g = 1; g < G; ++g) {  // cut where the cumulative sample count passes g / G of the total
+            const long long cut = sample_offsets[0] + total * g / G;
+            while (b < B - (G - g) && sample_offsets[b + 1] <= cut) ++b;
+            if (b <= pipe.first[g - 1]) b = pipe.first[g - 1] + 1;
+            pipe.first[g] = b;
+        }
+        pipe.first[G] = B;
+        for (int g = 0; g < G; ++g) pipe.copied[g] = h->copied[g];
+    }
+    auto issue_copies = [&]() -> int {
+        NB_CUDA(cudaEventRecord(h->fork_event, st));  // the staging area may still be read by earlier work on st
+        NB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->fork_event, 0));
+        for (int g = 0; g < pipe.n_groups; ++g) {
+            const long long s0 = sample_offsets[pipe.first[g]], s1 = sample_offsets[pipe.first[g + 1]];
+            NB_CUDA(cudaMemcpyAsync(wav_dev + (s0 - sample_offsets[0]), wav_host + s0, (size_t)(s1 - s0) * 4,
+                                    cudaMemcpyHostToDevice, h->copy_stream));
+            NB_CUDA(cudaEventRecord(h->copied[g], h->copy_stream));
+        }
+        return 0;
+    };
+    NB_TRY(embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, core, stream, &pipe, issue_copies));
     NB_CUDA(cudaMemcpyAsync(emb_host, emb_dev, (size_t)B * EMB * 4, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
     return 0;

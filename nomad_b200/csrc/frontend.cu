@@ -16,9 +16,9 @@ namespace nb {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wav,
-                                                         const UttMeta* __restrict__ meta, int max_chunks,
+                                                         const UttMeta* __restrict__ meta, int b0, int max_chunks,
                                                          double* __restrict__ part) {
-    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int b = b0 + blockIdx.y, chunk = blockIdx.x;
     const UttMeta m = meta[b];
     const int t_begin = chunk * STAT_CHUNK;
     if (t_begin >= m.T0) return;
@@ -57,9 +57,10 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
     }
 }
 
-int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int B, int max_chunks, double* part) {
-    dim3 grid(max_chunks, B);
-    wave_stats_kernel<<<grid, 256, 0, st>>>(wav, meta, max_chunks, part);
+int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int b0, int nb, int max_chunks,
+                      double* part) {
+    dim3 grid(max_chunks, nb);
+    wave_stats_kernel<<<grid, 256, 0, st>>>(wav, meta, b0, max_chunks, part);
     NB_LAUNCHED();
     return 0;
 }
@@ -67,11 +68,11 @@ int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, in
 // ---------------------------------------------------------------------------------------------
 // fold[b][c][0..9] = w[c][j] * rstd * gamma,  fold[b][c][10] = beta - mean * rstd * gamma
 __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__ part,
-                                                      const UttMeta* __restrict__ meta, int max_chunks,
+                                                      const UttMeta* __restrict__ meta, int b0, int max_chunks,
                                                       const float* __restrict__ w0, const float* __restrict__ gn_g,
                                                       const float* __restrict__ gn_b, float* __restrict__ fold,
                                                       float* __restrict__ stat_out, op_t* __restrict__ fold_h) {
-    const int b = blockIdx.x;
+    const int b = b0 + blockIdx.x;
     const UttMeta m = meta[b];
     __shared__ double s[NSTAT];
     if (threadIdx.x < NSTAT) {
@@ -126,10 +127,10 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
     }
 }
 
-int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
+int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int b0, int nb, int max_chunks,
                    const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out,
                    op_t* fold_h) {
-    gn_fold_kernel<<<B, 512, 0, st>>>(part, meta, max_chunks, conv0_w, gn_g, gn_b, fold, stat_out, fold_h);
+    gn_fold_kernel<<<nb, 512, 0, st>>>(part, meta, b0, max_chunks, conv0_w, gn_g, gn_b, fold, stat_out, fold_h);
     NB_LAUNCHED();
     return 0;
 }
@@ -141,12 +142,13 @@ int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int
 static constexpr int C0_ROWS = 64;
 
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav,
-                                                          const UttMeta* __restrict__ meta, int B,
+                                                          const UttMeta* __restrict__ meta, int B, int blk0,
                                                           const float* __restrict__ fold, op_t* __restrict__ out,
                                                           op_t* __restrict__ aux_out) {
-    const int row_base = blockIdx.x * C0_ROWS;
+    const int blk = blk0 + blockIdx.x;
+    const int row_base = blk * C0_ROWS;
     // utterance lookup: frame-level offsets are row offsets / 64
-    const int b = find_utt_by_frame(meta, B, blockIdx.x);
+    const int b = find_utt_by_frame(meta, B, blk);
     const UttMeta m = meta[b];
     const int t_base = row_base - m.row0;
     __shared__ float xs[C0_ROWS * 5 + 8];
@@ -250,10 +252,11 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
 }
 
 __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
-                                                        int B, const float* __restrict__ fold,
+                                                        int B, int blk0, const float* __restrict__ fold,
                                                         const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
-    const int row_base = blockIdx.x * C0_ROWS;
-    const int b = find_utt_by_frame(meta, B, blockIdx.x);
+    const int blk = blk0 + blockIdx.x;
+    const int row_base = blk * C0_ROWS;
+    const int b = find_utt_by_frame(meta, B, blk);
     const UttMeta m = meta[b];
     const int t_base = row_base - m.row0;
     __shared__ float xs[C0_ROWS * 5 + 16];
@@ -326,15 +329,18 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
     }
 }
 
-int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
-                       const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out) {
+int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long row_begin,
+                       long long row_end, const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out) {
     static const int use_mma = getenv("NOMAD_B200_CONV0_MMA") ? atoi(getenv("NOMAD_B200_CONV0_MMA")) : 1;
+    const unsigned blocks = (unsigned)((row_end - row_begin) / C0_ROWS);
+    const int blk0 = (int)(row_begin / C0_ROWS);
+    if (blocks == 0) return 0;
     if (aux_out == nullptr && fold_h != nullptr && use_mma) {
-        conv0_mma_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, fold_h, out);
+        conv0_mma_kernel<<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
         NB_LAUNCHED();
         return 0;
     }
-    conv0_apply_kernel<<<(unsigned)(rows0 / C0_ROWS), 256, 0, st>>>(wav, meta, B, fold, out, aux_out);
+    conv0_apply_kernel<<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, out, aux_out);
     NB_LAUNCHED();
     return 0;
 }

@@ -5,12 +5,15 @@
 namespace nb {
 
 // ---- frontend.cu: waveform -> conv0 + GroupNorm + GELU, LayerNorm(512)
-int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int B, int max_chunks, double* part);
-int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int B, int max_chunks,
+// utterances [b0, b0 + nb)
+int launch_wave_stats(cudaStream_t st, const float* wav, const UttMeta* meta, int b0, int nb, int max_chunks,
+                      double* part);
+int launch_gn_fold(cudaStream_t st, const double* part, const UttMeta* meta, int b0, int nb, int max_chunks,
                    const float* conv0_w, const float* gn_g, const float* gn_b, float* fold, float* stat_out,
                    op_t* fold_h);
-int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long rows0,
-                       const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out);
+// level-0 rows [row_begin, row_end) (multiples of 64, utterance boundaries)
+int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long row_begin,
+                       long long row_end, const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out);
 // zero rows [T_l, rows_l) of every utterance at conv level l (so masked rows carry no gradient)
 int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B, int level);
 int launch_ln512(cudaStream_t st, const op_t* in, long long rows, const float* g, const float* b, op_t* out);

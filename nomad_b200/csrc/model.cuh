@@ -129,12 +129,22 @@ struct Handle {
     char* meta_host = nullptr;  // pinned staging for the per-call metadata (UttMeta[B] + attention work list)
     size_t meta_cap = 0;        // bytes per staging slot
     cudaEvent_t meta_event = nullptr;  // last use of meta_host by an async copy
+    cudaStream_t copy_stream = nullptr;  // H2D side stream of the *_host entry points
+    cudaEvent_t fork_event = nullptr;
+    cudaEvent_t copied[8] = {};
 };
 
 int make_plan(const int64_t* sample_offsets, int B, Plan* plan);
 size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save);
+// Host-buffer entry points copy the waveform in utterance groups on a side stream; the front end (statistics, conv0,
+// conv1) of group g then runs while group g + 1 is still crossing PCIe.
+struct FrontPipe {
+    int n_groups = 0;
+    int first[9] = {0};          // group g = utterances [first[g], first[g + 1])
+    cudaEvent_t copied[8] = {};  // recorded on the copy stream after group g's H2D copy
+};
 int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* wav, cudaStream_t st, float* layers_out,
-                    int layer_T);
+                    int layer_T, const FrontPipe* pipe = nullptr);
 int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st);
 void build_attention_items(const Plan& p, std::vector<uint32_t>* items);
 GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld);

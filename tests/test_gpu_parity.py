@@ -316,6 +316,13 @@ def test_mixed_long_short_batch_against_oracle(engine, state_dict):
     emb = engine.embed(waves).cpu().numpy()
     ref = O.embed_each(state_dict, waves).numpy()
     assert np.abs(emb - ref).max() <= EMB_TOL
+    # host-buffer entry point: the H2D copy is pipelined in utterance groups against the front end; same bits,
+    # also for fewer utterances than copy groups
+    flat = np.ascontiguousarray(torch.cat(waves).numpy())
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    np.testing.assert_array_equal(engine.embed_host(flat, off), emb)
+    np.testing.assert_array_equal(engine.embed_host(flat[: off[2]], off[:3]), engine.embed(waves[:2]).cpu().numpy())
 
 
 # ------------------------------------------------------------------------------------------- loss
