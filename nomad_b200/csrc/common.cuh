@@ -188,6 +188,28 @@ __device__ __forceinline__ void stage_flush_f32(const float* stage, float* out, 
     }
     __syncwarp();
 }
+// Reverse direction for an fp32 tile of which every lane needs one ROW (the residual stream in a GEMM epilogue):
+// cp.async moves 16-byte pieces global -> shared with consecutive lanes on consecutive pieces of the same row
+// (whole sectors per request, no registers held while the data is in flight); after stage_fill_wait each lane reads
+// its own row back (swizzled, conflict-free).  All 32 rows x 32 columns must be valid.
+__device__ __forceinline__ void stage_fill_f32_async(float* stage, const float* src, long long ld, int lane) {
+    const int p = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rl = k * 4 + (lane >> 3);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stage + rl * 32 + ((p ^ (rl & 7)) << 2))),
+                     "l"(src + rl * ld + p * 4)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_fill_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+__device__ __forceinline__ float4 stage_row_f32(const float* stage, int lane, int p) {
+    return *reinterpret_cast<const float4*>(stage + lane * 32 + ((p ^ (lane & 7)) << 2));
+}
 __device__ __forceinline__ void stage_put_h16(op_t* stage, const float (&v)[32], int lane) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)

@@ -59,6 +59,12 @@ __device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, u
 struct RowCtx {
     float2 st;       // (mean, rstd) of the LayerNorm input row (EPI_LN_FOLD / EPI_RESID_LN)
     float pm, pM2;   // statistics of the previous (even) 32-column chunk (EPI_STATS_OUT)
+    // Residual prefetch (8-warp pair kernel): this chunk's fp32 residual tile was requested with cp.async into
+    // `rbuf` one chunk (or, for the first chunk of a tile, one mainloop) ago; as soon as it has been consumed the
+    // next chunk's tile is requested from `rnext` (nullptr: nothing to prefetch / this chunk was not prefetched).
+    float* rbuf;
+    bool rhave;
+    const float* rnext;
 };
 // (mean, rstd) of a 768-wide row from its LN_PARTS partial (mean, M2) pairs of 64 columns each (Chan et al.)
 __device__ __forceinline__ float2 ln_row_stats(const float* part, long long row) {
@@ -144,13 +150,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
+    const bool rpf = FULL && rc.rhave;  // warp-uniform
+    if (rpf) stage_fill_wait();
     if ((FULL || row_ok) && (flags & EPI_RESID)) {
         const float4* rp =
             reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0 + (long long)b * e.resid_bstride);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 t = __ldg(rp + j);
+                const float4 t = rpf ? stage_row_f32(rc.rbuf, lane, j) : __ldg(rp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
         }
@@ -165,13 +173,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 t = __ldg(rp + j), g = __ldg(gp + j), bb = __ldg(bp + j);
+                const float4 t = rpf ? stage_row_f32(rc.rbuf, lane, j) : __ldg(rp + j), g = __ldg(gp + j), bb = __ldg(bp + j);
                 v[4 * j + 0] += fmaf((t.x - st.x) * st.y, g.x, bb.x);
                 v[4 * j + 1] += fmaf((t.y - st.x) * st.y, g.y, bb.y);
                 v[4 * j + 2] += fmaf((t.z - st.x) * st.y, g.z, bb.z);
                 v[4 * j + 3] += fmaf((t.w - st.x) * st.y, g.w, bb.w);
             }
         }
+    }
+    if (rc.rbuf != nullptr) {  // warp-uniform
+        if (rpf) __syncwarp();  // every lane has read its row
+        rc.rhave = rc.rnext != nullptr;
+        if (rc.rhave) stage_fill_f32_async(rc.rbuf, rc.rnext, e.ldr, lane);
     }
     if (flags & EPI_STATS_OUT) {  // two-pass statistics of this chunk, merged pairwise into 64-column partials
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -320,7 +333,7 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 template <int CHUNKS, bool PAIR, bool CDIST>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
-                                              float2 row_st) {
+                                              float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src) {
     const bool row_ok = row < args.M;
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
@@ -328,6 +341,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
     RowCtx rc;
     rc.st = row_st;
     rc.pm = rc.pM2 = 0.f;
+    rc.rbuf = rbuf;
+    rc.rhave = rhave;
+    rc.rnext = nullptr;
 #pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
@@ -344,6 +360,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
         int ncols = args.N - col0;
         ncols = ncols > 32 ? 32 : ncols;
         if (ccol_first + c * 32 >= args.umma_n) ncols = 0;
+        if (!CDIST && rbuf != nullptr) {  // where the residual tile of the NEXT chunk (or tile) comes from
+            rc.rnext = next_tile_src;
+            if (c + 1 < CHUNKS) {
+                const int col1 = col0 + 32;
+                rc.rnext = (rows_valid == 32 && col1 + 32 <= args.N && ccol_first + (c + 1) * 32 + 32 <= args.umma_n)
+                               ? args.epi.resid + (row - lane) * args.epi.ldr + col1
+                               : nullptr;
+            }
+        }
         if (ncols > 0 && rows_valid > 0) {  // warp-uniform
             float v[32];
 #pragma unroll
@@ -353,6 +378,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
             else epilogue_chunk<false>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
+    rhave = rc.rhave;
     if (CDIST && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
 }
 
@@ -464,6 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h = ew >> 2;           // column half
         constexpr int HALF = BN / 2;
         constexpr int CHUNKS = (HALF + 31) / 32;
+        bool no_prefetch = false;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int n_blk = tile % args.n_tiles;
@@ -477,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             epilogue_tile<CHUNKS, false, CDIST>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                         row_st);
+                                         row_st, nullptr, no_prefetch, nullptr);
         }
     }
     tc_fence_before();
@@ -501,10 +528,16 @@ struct Pair256 {
     static constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of B
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = 5;
-    static constexpr int smem_bytes(int epi_warps) { return STAGES * STAGE_BYTES + epi_warps * 4096 + 1024 + 256; }
+    // + one 4 KB residual-prefetch buffer per epilogue warp in the RPF instantiation (8 warps only: the 16-warp
+    // variant has no room).  It is a separate instantiation so that GEMMs without a residual keep the smaller
+    // shared-memory carve-out (and with it 60 KB instead of 28 KB of L1 for their epilogue's vector loads).
+    static constexpr int resid_bytes(int epi_warps, bool rpf) { return rpf ? epi_warps * 4096 : 0; }
+    static constexpr int smem_bytes(int epi_warps, bool rpf) {
+        return STAGES * STAGE_BYTES + epi_warps * 4096 + resid_bytes(epi_warps, rpf) + 1024 + 256;
+    }
 };
 
-template <int NEW, bool CDIST>  // NEW = epilogue warps (8 or 16)
+template <int NEW, bool CDIST, bool RPF>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     using Cfg = Pair256;
@@ -513,7 +546,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096);
+    float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -609,6 +643,24 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;
         const int h = ew >> 2;
         constexpr int HALF = BN / (NEW / 4);  // columns per epilogue warp (two or four column groups)
+        // residual prefetch: first 32 x 32 fp32 tile of this warp in tile t (nullptr if it is ragged / absent)
+        const bool want_pf = RPF && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1;
+        float* rbuf = want_pf ? resid_stage + ew * 1024 : nullptr;
+        auto tile_src = [&](int t) -> const float* {
+            if (!want_pf || t >= num_tiles) return nullptr;
+            const int n2 = t % args.n_tiles, m2 = (t / args.n_tiles) % args.m_tiles;
+            const long long r0 = (long long)m2 * 256 + rank * BM + q * 32;
+            const int c0 = n2 * BN + h * HALF;
+            return (r0 + 32 <= args.M && c0 + 32 <= args.N) ? args.epi.resid + r0 * args.epi.ldr + c0 : nullptr;
+        };
+        bool rhave = false;
+        if (want_pf) {
+            const float* src = tile_src(pair_id);
+            if (src != nullptr) {
+                stage_fill_f32_async(rbuf, src, args.epi.ldr, lane);
+                rhave = true;
+            }
+        }
         int it = 0;
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
             const int n_blk = tile % args.n_tiles;
@@ -618,9 +670,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t aphase = (it >> 1) & 1;
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
             const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
-            if (!CDIST && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
-                // pull the NEXT tile's slice of the fp32 residual stream into L2 now, a whole mainloop ahead of
-                // its use: the epilogue's row loads then pay L2 latency instead of HBM latency
+            if (!CDIST && !want_pf && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
+                // no prefetch buffer (16-warp variant): at least pull the NEXT tile's slice of the fp32 residual
+                // stream into L2 a whole mainloop ahead of its use
                 const int nt = tile + num_pairs;
                 const int n2 = nt % args.n_tiles, m2 = (nt / args.n_tiles) % args.m_tiles;
                 const long long r2 = (long long)m2 * 256 + rank * BM + q * 32 + lane;
@@ -628,11 +680,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (r2 < args.M && c2 + HALF <= args.N)
                     prefetch_l2_bulk(args.epi.resid + r2 * args.epi.ldr + c2, HALF * 4);
             }
+            const float* next_src = tile_src(tile + num_pairs);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             epilogue_tile<HALF / 32, true, CDIST>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                           row_st);
+                                           row_st, rbuf, rhave, next_src);
         }
     }
     tc_fence_before();
@@ -806,13 +859,13 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
 }
 
-template <int NEW, bool CDIST>
+template <int NEW, bool CDIST, bool RPF = false>
 static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
-    constexpr int SMEM = Cfg::smem_bytes(NEW);
+    constexpr int SMEM = Cfg::smem_bytes(NEW, RPF);
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -825,7 +878,7 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_pair_kernel<NEW, CDIST><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
+    gemm_tc_pair_kernel<NEW, CDIST, RPF><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
@@ -844,6 +897,8 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     const bool heavy = args.K <= 1024 && ((fl & (EPI_GELU | EPI_SAVE_DGELU)) != 0 ||
                                           ((fl & (EPI_RESID | EPI_RESID_LN)) != 0 && !(fl & EPI_STATS_OUT)));
     if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
+    static const int rpf = getenv("NOMAD_B200_RESID_PREFETCH") ? atoi(getenv("NOMAD_B200_RESID_PREFETCH")) : 1;
+    if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) return launch_pair_impl<8, false, true>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
 
