@@ -78,6 +78,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 struct FaItem {
     int h, q0, T, n_kv;
     long long frame0;
@@ -230,14 +236,18 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                         uint32_t r[32];
                         tmem_ld_32x32(trow + c * 32, r);
                         tmem_ld_wait();
-                        if (c * 32 + 32 <= nv) {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
-                        } else {
+                        if (c * 32 + 32 > nv) {  // partial chunk: mask once
 #pragma unroll
                             for (int k = 0; k < 32; ++k)
-                                if (c * 32 + k < nv) mx = fmaxf(mx, __uint_as_float(r[k]));
+                                if (c * 32 + k >= nv) r[k] = 0xff800000u;  // -inf
                         }
+                        float m2[2] = {mx, -INFINITY};  // FMNMX3: two scores per instruction
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            m2[0] = max3(m2[0], __uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+                            m2[1] = max3(m2[1], __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+                        }
+                        mx = fmaxf(m2[0], m2[1]);
                     }
                 }
                 const float m_new = fmaxf(m_run, mx);
@@ -268,11 +278,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                         tmem_ld_wait();
                         float p[32];
                         if (c * 32 + 32 <= nv) {
+                            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int k = 0; k < 32; ++k) {
                                 p[k] = ex2_approx(fmaf(__uint_as_float(r[k]), LOG2E, -ms));
-                                sum += p[k];
+                                s4[k & 3] += p[k];
                             }
+                            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
                         } else {
 #pragma unroll
                             for (int k = 0; k < 32; ++k) {

@@ -107,19 +107,24 @@ __global__ void __launch_bounds__(512) gn_fold_kernel(const double* __restrict__
     for (int j = 0; j < 10; ++j) o[j] = (float)(w[j] * a);
     o[10] = (float)((double)gn_b[c] - mean * a);
     o[11] = (float)a;  // gamma * rstd, folded into the saved GELU gradient for the loss backward
-    if (fold_h != nullptr) {  // 16-bit taps for the tensor-core conv0 (B operand of mma.sync), K padded to 16:
-        // halves [0, 16) = hi part, [16, 32) = lo part (tap - hi), so hi + lo carries 22 bits of each tap
+    if (fold_h != nullptr) {  // 16-bit taps for the tensor-core conv0 (B operands of two mma.sync k-steps, see there)
         uint32_t* h = reinterpret_cast<uint32_t*>(fold_h + ((long long)b * CONV_DIM + c) * 32);
+        uint32_t hi[5], lo[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const float t0 = (float)(w[2 * j] * a), t1 = (float)(w[2 * j + 1] * a);
-            const uint32_t hi = pack_op(t0, t1);
-            const float2 hf = unpack_op(hi);
-            h[j] = hi;
-            h[8 + j] = pack_op(t0 - hf.x, t1 - hf.y);
+            hi[j] = pack_op(t0, t1);
+            const float2 hf = unpack_op(hi[j]);
+            lo[j] = pack_op(t0 - hf.x, t1 - hf.y);
         }
-        h[5] = 0u; h[6] = 0u; h[7] = 0u;
-        h[13] = 0u; h[14] = 0u; h[15] = 0u;
+        // k-step 1: [wh0..wh9 | wh0..wh5]      k-step 2: [wh6..wh9 | wl0..wl9 | 0 0]
+#pragma unroll
+        for (int j = 0; j < 5; ++j) h[j] = hi[j];
+        h[5] = hi[0]; h[6] = hi[1]; h[7] = hi[2];
+        h[8] = hi[3]; h[9] = hi[4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) h[10 + j] = lo[j];
+        h[15] = 0u;
     }
     if (stat_out != nullptr) {
         stat_out[((long long)b * CONV_DIM + c) * 2 + 0] = (float)mean;
@@ -241,7 +246,10 @@ int launch_zero_pad_rows(cudaStream_t st, op_t* buf, const UttMeta* meta, int B,
 // fp16 carries 11 bits, 16-bit PCM and trained band-pass taps need more: on real speech a plain fp16 product was
 // measured 3-80x noisier than the fp16 rounding of the output (a filter's stop-band leakage scales with the
 // quantisation of its taps and of the samples).  So samples and taps are split x = xh + xl, w = wh + wl and
-// the product is three MMAs, xh wh + xl wh + xh wl (error ~2^-22, below fp32 accumulation noise).
+// the product is xh wh + xl wh + xh wl (error ~2^-22, below fp32 accumulation noise): 30 products per output,
+// packed into TWO k = 16 steps --
+//   step 1: K slots 0..9 = xh_j wh_j,  10..15 = xl_j wh_j (j = 0..5)
+//   step 2: K slots 0..3 = xl_j wh_j (j = 6..9),  4..13 = xh_j wl_j,  14..15 unused (zero taps).
 // One block = 64 frames x 512 channels, warp w owns channels [64 w, 64 w + 64).  The scalar kernel above spends
 // 20 of its ~27 instructions per element on FMAs and shared loads; here the FMAs are 32 mma per warp and what
 // remains is the GELU.  Lanes of a quad trade halves so every store instruction writes full 32 B sectors.
@@ -285,16 +293,33 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
     const int valid = m.T0 - t_base;
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
-        uint32_t af[4], al[4];
+        // A fragments of the two k-steps: a[0], a[1] = K slots 2q, 2q+1 of rows r, r+8; a[2], a[3] = slots 2q+8, 2q+9
+        uint32_t a1[4], a2[4];
         {
-            const int i0 = 5 * (mt * 16 + r) + 2 * q, i1 = i0 + 40;  // rows r and r + 8
-            const int idx[4] = {i0, i1, i0 + 8, i1 + 8};
+            const int ib[2] = {5 * (mt * 16 + r), 5 * (mt * 16 + r) + 40};  // first sample of rows r and r + 8
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float x0 = xs[idx[k]], x1 = xs[idx[k] + 1];
-                af[k] = pack_op(x0, x1);
-                const float2 hf = unpack_op(af[k]);
-                al[k] = pack_op(x0 - hf.x, x1 - hf.y);
+            for (int k = 0; k < 2; ++k) {
+                const float* x = xs + ib[k];
+                // step 1, slots 2q, 2q+1: xh[2q], xh[2q+1]
+                a1[k] = pack_op(x[2 * q], x[2 * q + 1]);
+                // step 1, slots 2q+8, 2q+9: q = 0 -> xh[8], xh[9];  q >= 1 -> xl[2q-2], xl[2q-1]
+                {
+                    const int o = q == 0 ? 8 : 2 * q - 2;
+                    const float x0 = x[o], x1 = x[o + 1];
+                    const uint32_t hh = pack_op(x0, x1);
+                    const float2 hf = unpack_op(hh);
+                    a1[2 + k] = q == 0 ? hh : pack_op(x0 - hf.x, x1 - hf.y);
+                }
+                // step 2, slots 2q, 2q+1: q < 2 -> xl[6+2q], xl[7+2q];  q >= 2 -> xh[2q-4], xh[2q-3]
+                {
+                    const int o = q < 2 ? 6 + 2 * q : 2 * q - 4;
+                    const float x0 = x[o], x1 = x[o + 1];
+                    const uint32_t hh = pack_op(x0, x1);
+                    const float2 hf = unpack_op(hh);
+                    a2[k] = q < 2 ? pack_op(x0 - hf.x, x1 - hf.y) : hh;
+                }
+                // step 2, slots 2q+8, 2q+9 = xh[2q+4], xh[2q+5] (q = 3: slots 14, 15 meet zero taps)
+                a2[2 + k] = pack_op(x[2 * q + 4], x[2 * q + 5]);
             }
         }
         const int row0 = mt * 16 + r, row1 = row0 + 8;
@@ -304,12 +329,10 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
         for (int np = 0; np < 4; ++np) {  // pairs of channel tiles: 16 channels = 32 B per row per quad
             float c0[4] = {sh[2 * np][0], sh[2 * np][1], sh[2 * np][0], sh[2 * np][1]};
             float c1[4] = {sh[2 * np + 1][0], sh[2 * np + 1][1], sh[2 * np + 1][0], sh[2 * np + 1][1]};
-            mma_f16_16816(c0, al, bf[2 * np][0], bf[2 * np][1]);
-            mma_f16_16816(c1, al, bf[2 * np + 1][0], bf[2 * np + 1][1]);
-            mma_f16_16816(c0, af, bl[2 * np][0], bl[2 * np][1]);
-            mma_f16_16816(c1, af, bl[2 * np + 1][0], bl[2 * np + 1][1]);
-            mma_f16_16816(c0, af, bf[2 * np][0], bf[2 * np][1]);
-            mma_f16_16816(c1, af, bf[2 * np + 1][0], bf[2 * np + 1][1]);
+            mma_f16_16816(c0, a2, bl[2 * np][0], bl[2 * np][1]);
+            mma_f16_16816(c1, a2, bl[2 * np + 1][0], bl[2 * np + 1][1]);
+            mma_f16_16816(c0, a1, bf[2 * np][0], bf[2 * np][1]);
+            mma_f16_16816(c1, a1, bf[2 * np + 1][0], bf[2 * np + 1][1]);
             // packed pairs: e = tile 2np (cols 2q, 2q+1), f = tile 2np+1, rows row0 / row1
             uint32_t e0 = pack_op(gelu_act(c0[0]), gelu_act(c0[1])), e1 = pack_op(gelu_act(c0[2]), gelu_act(c0[3]));
             uint32_t f0 = pack_op(gelu_act(c1[0]), gelu_act(c1[1])), f1 = pack_op(gelu_act(c1[2]), gelu_act(c1[3]));
