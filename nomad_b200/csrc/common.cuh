@@ -164,6 +164,23 @@ __device__ __forceinline__ float2 unpack_op(uint32_t u) {
     __half2 v = *reinterpret_cast<__half2*>(&u);
     return __half22float2(v);
 }
+// Two GELUs straight to a packed fp16 pair with ONE MUFU for both: sigma(2u) = (1 + tanh u) / 2 with the same
+// minimax u(x), tanh.approx.f16x2 on the packed arguments, and the final 0.5 x (1 + t) as one HFMA2.  Error is that
+// of fp16 tanh (~5e-4 absolute on t, i.e. <= 2.5e-4 |x| on the result): about one extra fp16 rounding.  Only used
+// where the MUFU pipe is the bound and the result is stored as fp16 anyway (conv0: 1.7 G activations per step).
+__device__ __forceinline__ uint32_t gelu_pair_h2(float x0, float x1) {
+    const float a0 = fminf(x0 * x0, 36.0f), a1 = fminf(x1 * x1, 36.0f);
+    float p0 = fmaf(-3.515167885e-04f, a0, 3.700564602e-02f), p1 = fmaf(-3.515167885e-04f, a1, 3.700564602e-02f);
+    p0 = fmaf(p0, a0, 7.975078843e-01f);
+    p1 = fmaf(p1, a1, 7.975078843e-01f);
+    const uint32_t u = pack_op(x0 * p0, x1 * p1);
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+    const uint32_t hx = pack_op(0.5f * x0, 0.5f * x1);
+    uint32_t r;
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(hx), "r"(t));
+    return r;
+}
 
 // ---------------------------------------------------------------- row-per-lane -> coalesced stores via smem
 static constexpr int STAGE_BYTES_PER_WARP = 4096;

@@ -12,6 +12,10 @@
 
 #include "kernels.cuh"
 
+#ifndef NB_CONV0_GELU_H2
+#define NB_CONV0_GELU_H2 1
+#endif
+
 namespace nb {
 
 // ---------------------------------------------------------------------------------------------
@@ -334,8 +338,13 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
             mma_f16_16816(c0, a1, bf[2 * np][0], bf[2 * np][1]);
             mma_f16_16816(c1, a1, bf[2 * np + 1][0], bf[2 * np + 1][1]);
             // packed pairs: e = tile 2np (cols 2q, 2q+1), f = tile 2np+1, rows row0 / row1
+#if NB_CONV0_GELU_H2
+            uint32_t e0 = gelu_pair_h2(c0[0], c0[1]), e1 = gelu_pair_h2(c0[2], c0[3]);
+            uint32_t f0 = gelu_pair_h2(c1[0], c1[1]), f1 = gelu_pair_h2(c1[2], c1[3]);
+#else
             uint32_t e0 = pack_op(gelu_act(c0[0]), gelu_act(c0[1])), e1 = pack_op(gelu_act(c0[2]), gelu_act(c0[3]));
             uint32_t f0 = pack_op(gelu_act(c1[0]), gelu_act(c1[1])), f1 = pack_op(gelu_act(c1[2]), gelu_act(c1[3]));
+#endif
             // lane q stores channels 4q..4q+3 of the 16: q<2 -> from tile 2np lanes (2q, 2q+1); q>=2 -> tile 2np+1
             const int src = (lane & ~3) | ((2 * q) & 3);
             const uint32_t a_e0 = __shfl_sync(0xffffffffu, e0, src), b_e0 = __shfl_sync(0xffffffffu, e0, src + 1);
