@@ -116,6 +116,15 @@ NOMAD_B200_API int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_
                          const float* bias, const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags,
                          int gemm_impl, void* stream);
 
+/* ---- ingest: ``Nomad.load_processing`` (nomad.py:192-212) after the file has been decoded to PCM ------------
+ * pcm: n_frames x channels interleaved int16 DEVICE samples at ``sr`` Hz.  out: mono fp32 at ``target_sr``:
+ * sample / 32768, mean of the first two channels when channels > 1 (nomad.py:199-200), torchaudio's default
+ * ``Resample(sr, target_sr)`` (sinc-Hann, width 6, rolloff 0.99; nomad.py:203-205) when the rates differ, cut to
+ * 10 s when ``trim`` (nomad.py:208-210).  ``nomad_b200_ingest_out_samples`` gives the output length (host only). */
+NOMAD_B200_API int64_t nomad_b200_ingest_out_samples(int64_t n_frames, int sr, int target_sr, int trim);
+NOMAD_B200_API int nomad_b200_ingest_pcm16(const int16_t* pcm_dev, int64_t n_frames, int channels, int sr, int target_sr, int trim,
+                            float* out_dev, void* stream);
+
 /* The attention core of one encoder layer, softmax(Q K^T) V per (utterance, head) (fairseq
  * MultiheadAttention inside TransformerSentenceEncoderLayer; mirror torchaudio components.py:237-330).
  * qkv: frames x 2304 op_t device (q | k | v per row, q already scaled by head_dim^-0.5); utterance u owns rows

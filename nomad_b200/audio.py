@@ -51,6 +51,32 @@ def load_wav(filepath: str):
         return torchaudio.load(filepath)
 
 
+def read_pcm16(filepath: str):
+    """-> ((n_frames, channels) int16 array, sample_rate) for a 16-bit PCM wav, else None."""
+    try:
+        with wave.open(str(filepath), "rb") as w:
+            if w.getsampwidth() != 2:
+                return None
+            ch, sr, n = w.getnchannels(), w.getframerate(), w.getnframes()
+            raw = w.readframes(n)
+        return np.frombuffer(raw, dtype="<i2").reshape(-1, ch), sr
+    except (wave.Error, EOFError):
+        return None
+
+
+def load_processing_device(engine, filepath, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
+    """``load_processing`` with the sample conversion, channel mix, resampling and trim on the GPU
+    (``nomad_b200_ingest_pcm16``) for 16-bit PCM wavs -- the 16-bit samples are what crosses PCIe; any other file
+    takes the host path below and is moved to the device.  Returns a (1, N) fp32 CUDA tensor."""
+    if isinstance(filepath, np.ndarray):
+        filepath = filepath[0]
+    got = read_pcm16(filepath)
+    if got is None:
+        return load_processing(filepath, target_sr, trim).to(engine.device)
+    pcm, sr = got
+    return engine.ingest_pcm16(pcm, sr, target_sr, trim)
+
+
 def load_processing(filepath, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
     """Mono 16 kHz float32 (1, N): mean of the first two channels if multi-channel
     (``nomad.py:199-200``), resample if needed (``:203-205``), optional 10 s trim (``:208-210``)."""

@@ -140,6 +140,23 @@ class Engine:
                        "nomad_b200_embed_host")
         return emb_host
 
+    # ------------------------------------------------------------------ ingest
+    def ingest_pcm16(self, pcm: np.ndarray, sr: int, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
+        """``load_processing`` on the device: (n_frames, channels) or (n_frames,) int16 HOST samples at ``sr`` ->
+        (1, N) fp32 CUDA tensor at ``target_sr`` (mono mix, torchaudio-default resampling, optional 10 s trim)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if pcm.ndim == 1:
+            pcm = pcm[:, None]
+        n, ch = pcm.shape
+        n_out = int(self.lib.nomad_b200_ingest_out_samples(n, int(sr), int(target_sr), 1 if trim else 0))
+        out = torch.empty((1, max(n_out, 0)), dtype=torch.float32, device=self.device)
+        if n_out > 0:
+            dev = torch.from_numpy(pcm if pcm.flags.writeable else pcm.copy()).to(self.device, non_blocking=True)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.nomad_b200_ingest_pcm16(_ptr(dev), n, ch, int(sr), int(target_sr), 1 if trim else 0,
+                                                            _ptr(out), _stream_ptr()), "nomad_b200_ingest_pcm16")
+        return out
+
     # ------------------------------------------------------------------ loss-side forward
     def num_frames(self, n: int) -> int:
         return int(self.lib.nomad_b200_num_frames(int(n)))

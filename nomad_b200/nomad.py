@@ -174,6 +174,7 @@ class Nomad():
         # fairseq applies GradMultiply(feature_grad_mult) to the conv features (wav2vec 2.0 base: 0.1)
         self.feature_grad_mult = float(feature_grad_mult)
         self.max_batch_samples = int(max_batch_seconds * 16000)
+        self.device_ingest = os.environ.get("NOMAD_B200_DEVICE_INGEST", "1") != "0"
 
     def predict(self, mode='dir', nmr='data/nmr-data', deg='data/test-data', results_path=None):
         if nmr is None:
@@ -283,7 +284,10 @@ class Nomad():
                 filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
             else:
                 filepath = filename_anchor
-            wave = self.load_processing(filepath, trim=False)
+            # 16-bit PCM wavs are converted / mixed / resampled on the GPU (nomad_b200_ingest_pcm16); same result as
+            # the host ``load_processing`` below, which every other format still takes
+            wave = (audio.load_processing_device(self.engine, filepath, trim=False) if self.device_ingest
+                    else self.load_processing(filepath, trim=False))
             if wave.shape[-1] < MIN_SAMPLES:
                 raise RuntimeError(f"Calculated padded input size per channel: ({wave.shape[-1]}). Kernel size: (10). "
                                    "Kernel size can't be greater than actual input size")

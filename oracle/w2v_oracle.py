@@ -198,3 +198,42 @@ def flops_embed(n_samples: int) -> float:
     return (2.0 * (5120 * T[0] + 786432 * (T[1] + T[2] + T[3] + T[4]) + 524288 * (T[5] + T[6]))
             + 786432.0 * T6 + 9437184.0 * T6
             + 12.0 * (4718592.0 * T6 + 9437184.0 * T6 + 3072.0 * T6 * T6) + 393216.0)
+
+
+def resample_kernel_bank(orig_freq: int, new_freq: int):
+    """torchaudio ``_get_sinc_resample_kernel`` restated in numpy float64 (sinc-Hann, width 6, rolloff 0.99),
+    including the float32 rounding of ``-p / new`` that its int64-arange / int division produces.
+    -> (float32 (new, K) bank, width, orig, new) with the rates reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    o, n = int(orig_freq) // g, int(new_freq) // g
+    lpw, rolloff = 6, 0.99
+    base = min(o, n) * rolloff
+    width = math.ceil(lpw * o / base)
+    idx = np.arange(-width, width + o, dtype=np.float64)[None, :] / o
+    tp = (np.arange(0, -n, -1, dtype=np.int64) / np.float32(n)).astype(np.float32).astype(np.float64)[:, None]
+    t = np.clip((tp + idx) * base, -lpw, lpw)
+    window = np.cos(t * math.pi / lpw / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    return (k * window * (base / o)).astype(np.float32), width, o, n
+
+
+def load_processing_pcm16(pcm: np.ndarray, sr: int, target_sr: int = 16000, trim: bool = False) -> np.ndarray:
+    """``Nomad.load_processing`` (``nomad.py:192-212``) from decoded 16-bit PCM (n_frames, channels): scale, mean of
+    the first two channels, torchaudio-default ``Resample``, optional 10 s trim.  -> float32 (N,)."""
+    x = np.asarray(pcm, dtype=np.float32) / np.float32(32768.0)
+    if x.ndim == 1:
+        x = x[:, None]
+    x = (x[:, 0] + x[:, 1]) / np.float32(2) if x.shape[1] > 1 else x[:, 0]
+    if sr != target_sr:
+        bank, width, o, n = resample_kernel_bank(sr, target_sr)
+        length = x.shape[0]
+        xp = np.concatenate([np.zeros(width, np.float32), x, np.zeros(width + o, np.float32)])
+        groups = (xp.shape[0] - bank.shape[1]) // o + 1
+        win = np.lib.stride_tricks.sliding_window_view(xp, bank.shape[1])[::o][:groups]
+        y = (win.astype(np.float64) @ bank.T.astype(np.float64)).astype(np.float32).reshape(-1)
+        x = y[: -(-n * length // o)]
+    if trim and x.shape[0] > target_sr * 10:
+        x = x[: target_sr * 10]
+    return x

@@ -195,6 +195,36 @@ def test_model_call_signature_matches_reference(state_dict, golden_dir):
     assert len(feats) == 13 and feats[0].shape == (3, 12, 768) and feats[12].shape == (3, 256)
 
 
+# ---------------------------------------------------------------------------------------- ingest
+def test_device_ingest_against_reference_fixture(engine, golden_dir, tmp_path):
+    """nomad_b200_ingest_pcm16 (PCM16 -> mono float -> torchaudio-default resample -> trim on the GPU) vs the
+    reference's own operations (fixture) and the oracle; tolerance 1e-6 (fp32 summation order), lengths exact."""
+    from nomad_b200 import audio
+    from oracle import w2v_oracle as O
+    g = np.load(os.path.join(golden_dir, "ref_ingest.npz"))
+    for i in range(int(g["n_cases"])):
+        pcm, sr, trim = g[f"pcm{i}"], int(g[f"sr{i}"]), bool(g[f"trim{i}"])
+        y = engine.ingest_pcm16(pcm, sr, 16000, trim)
+        assert y.shape == (1, int(g[f"len{i}"])) and y.is_cuda
+        y = y[0].cpu().numpy()
+        got = y if not trim else np.concatenate([y[:2000], y[-2000:]])
+        assert np.abs(got - g[f"out{i}"]).max() <= 1e-6, i
+        assert np.abs(y - O.load_processing_pcm16(pcm, sr, 16000, trim)).max() <= 1e-6, i
+    # through a wav file: device path == host path (``load_processing``), mono / stereo, 16 kHz passthrough is exact
+    for i in (1, 4):
+        pcm, sr = g[f"pcm{i}"], int(g[f"sr{i}"])
+        path = str(tmp_path / f"c{i}.wav")
+        with wave.open(path, "wb") as w:
+            w.setnchannels(pcm.shape[1]); w.setsampwidth(2); w.setframerate(sr); w.writeframes(pcm.tobytes())
+        dev = audio.load_processing_device(engine, path).cpu()
+        host = audio.load_processing(path)
+        assert dev.shape == host.shape
+        assert float((dev - host).abs().max()) <= (0.0 if sr == 16000 else 1e-6)
+    # empty and one-sample inputs
+    assert engine.ingest_pcm16(np.zeros((0, 1), np.int16), 44100).shape == (1, 0)
+    assert engine.ingest_pcm16(np.full((1, 1), 1234, np.int16), 48000).shape == (1, 1)
+
+
 # ------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("lengths", [
     [1, 2, 63, 64, 65, 127, 128, 129, 199, 256, 257, 511],   # every key-tile / query-tile edge
