@@ -107,6 +107,20 @@ NOMAD_B200_API int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const 
 NOMAD_B200_API int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nmr_host, int64_t m, float* dm_host,
                                double* row_mean_host, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- result formatting: ``df.round(3)`` + ``to_csv`` (nomad.py:113-120, 138-139) without pandas ------------------
+ * Writes ``index_name,col_labels...`` then one line per row: ``row_label,v,v,...`` with every value rounded like
+ * numpy (rint(x * 10^decimals) / 10^decimals; decimals < 0 = no rounding) and printed like Python's repr (shortest
+ * round-trip digits, "1.0", "1e-05"); NaN -> empty field, labels quoted like csv.QUOTE_MINIMAL.  The bytes equal
+ * what the reference's pandas calls write.  HOST pointers, host threads (0 = all cores); no GPU involved. */
+NOMAD_B200_API int nomad_b200_write_scores_csv(const char* path, const char* index_name, const char* const* row_labels,
+                                int64_t n_rows, const char* const* col_labels, int64_t n_cols, const double* values,
+                                int decimals, int threads);
+
+/* Paired distances d[i] = ||a[i] - b[i]|| (fp64 out): the diagonal of ``cdist`` that the reference's full-reference
+ * evaluation takes (src/training/train_triplet.py:267-274), without materialising the matrix.  a, b: n x 256 fp32
+ * device. */
+NOMAD_B200_API int nomad_b200_paired_dist(const float* a_dev, const float* b_dev, int64_t n, double* out_dev, void* stream);
+
 /* ---- building block exposed for the parity tests --------------------------------------------------
  * C (m x n, ldc) = epilogue(A (m x k op_t, row stride lda elements, may overlap) * B^T (n x k op_t)).
  * flags: 1 bias, 2 GELU(erf), 4 + residual fp32 (ld = ldc), 8 store fp32 (c_f32), 16 store op_t (c_f16).

@@ -42,6 +42,9 @@ PROTOTYPES = {
     "nomad_b200_cdist_mean_host": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
     "nomad_b200_gemm_f16": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
+    "nomad_b200_write_scores_csv": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), c_i64, C.POINTER(C.c_char_p),
+                                               c_i64, c_vp, C.c_int, C.c_int]),
+    "nomad_b200_paired_dist": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "nomad_b200_ingest_out_samples": (c_i64, [c_i64, C.c_int, C.c_int, C.c_int]),
     "nomad_b200_ingest_pcm16": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "nomad_b200_attention_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_int32), C.c_int]),
@@ -81,3 +84,19 @@ def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = load().nomad_b200_last_error().decode("utf-8", "replace")
         raise NomadB200Error(f"{what or 'nomad_b200 call'} failed: {msg}")
+
+
+def write_scores_csv(path, index_name, row_labels, col_labels, values, decimals=3, threads=0) -> None:
+    """``DataFrame(values, index=row_labels, columns=col_labels).round(decimals)`` + ``to_csv`` with ``index_name`` as
+    the first header cell, byte for byte, from a float64 (n, m) array -- nomad_b200_write_scores_csv."""
+    import numpy as np
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        values = values[:, None]
+    n, m = values.shape
+    assert len(row_labels) == n and len(col_labels) == m
+    rl = (C.c_char_p * max(n, 1))(*[str(x).encode("utf-8") for x in row_labels])
+    cl = (C.c_char_p * max(m, 1))(*[str(x).encode("utf-8") for x in col_labels])
+    check(load().nomad_b200_write_scores_csv(str(path).encode("utf-8"), str(index_name).encode("utf-8"), rl, n, cl, m,
+                                             values.ctypes.data_as(c_vp), int(decimals), int(threads)),
+          "nomad_b200_write_scores_csv")

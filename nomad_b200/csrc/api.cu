@@ -794,6 +794,11 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
     return 0;
 }
 
+int nomad_b200_paired_dist(const float* a_dev, const float* b_dev, int64_t n, double* out_dev, void* stream) {
+    NB_CHECK(n >= 0 && (n == 0 || (a_dev && b_dev && out_dev)), "paired_dist: bad arguments");
+    return launch_paired_dist((cudaStream_t)stream, a_dev, b_dev, n, out_dev);
+}
+
 size_t nomad_b200_attention_workspace_bytes(const int32_t* T, int n_utts) {
     size_t entries = 0;
     for (int u = 0; T != nullptr && u < n_utts; ++u) entries += (size_t)((T[u] + 127) / 128);

@@ -82,6 +82,36 @@ __global__ void __launch_bounds__(256) cdist_fp32_kernel(const float* __restrict
 }
 
 
+// Paired (diagonal-only) distances d[i] = ||a[i] - b[i]||_2 for the full-reference evaluation mode of the reference's
+// harness (train_triplet.py:267-274 takes the diagonal of cdist): one warp per pair, fp64 accumulation of the fp32
+// differences, so the result equals scipy's float64 cdist diagonal to rounding.
+__global__ void __launch_bounds__(256) paired_dist_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          long long n, double* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float4* pa = reinterpret_cast<const float4*>(a + row * CD_DIM);
+    const float4* pb = reinterpret_cast<const float4*>(b + row * CD_DIM);
+    double s = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float4 x = __ldg(pa + lane + 32 * h), y = __ldg(pb + lane + 32 * h);
+        const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y, d2 = (double)x.z - (double)y.z,
+                     d3 = (double)x.w - (double)y.w;
+        s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = sqrt(s);
+}
+
+int launch_paired_dist(cudaStream_t st, const float* a, const float* b, long long n, double* out) {
+    if (n <= 0) return 0;
+    paired_dist_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, b, n, out);
+    NB_LAUNCHED();
+    return 0;
+}
+
 __global__ void scale_rows_kernel(double* v, long long n, double s) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] *= s;

@@ -218,5 +218,16 @@ class Engine:
                                                       gemm_impl, _stream_ptr()), "nomad_b200_cdist_mean")
         return dm, mean
 
+    def paired_dist(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """(n, 256), (n, 256) fp32 -> (n,) fp64 distances of matching rows (the diagonal of ``cdist``)."""
+        a = a.to(self.device, torch.float32).contiguous()
+        b = b.to(self.device, torch.float32).contiguous()
+        assert a.shape == b.shape and a.shape[1] == EMB_DIM
+        out = torch.empty((a.shape[0],), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_paired_dist(_ptr(a), _ptr(b), a.shape[0], _ptr(out), _stream_ptr()),
+                       "nomad_b200_paired_dist")
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.nomad_b200_launch_count())

@@ -233,8 +233,12 @@ class Nomad():
             results_avg_path = os.path.join(results_path, 'nomad_avg.csv')
             results_scores_path = os.path.join(results_path, 'nomad_scores.csv')
 
-        df_avg_nomad.reset_index().to_csv(results_avg_path, index=False)
-        df_dm.reset_index().to_csv(results_scores_path, index=False)
+        # same bytes as ``df.reset_index().to_csv(path, index=False)`` (tests/test_host.py), written by the library's
+        # multi-threaded formatter from the unrounded values: pandas takes minutes on a 1e5 x 1e3 frame
+        from . import _lib
+        _lib.write_scores_csv(results_avg_path, 'Test File', test_files, ['NOMAD'], np.asarray(avg_nomad, dtype=np.float64))
+        _lib.write_scores_csv(results_scores_path, 'Test File', test_files, list(df_dm.columns),
+                              np.asarray(distance_matrix, dtype=np.float64))
         return df_avg_nomad, df_dm
 
     def pairwise(self, test_embeddings, nmr_embeddings):

@@ -295,6 +295,19 @@ def test_cdist_golden_and_properties(engine, golden_dir):
     assert float(z.diagonal().abs().max()) == 0.0
 
 
+def test_paired_distance_is_the_cdist_diagonal(engine):
+    """Full-reference mode of the reference's harness (train_triplet.py:267-274: ``np.diag(cdist(a, b))``)."""
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 1000):
+        a = rng.standard_normal((n, 256)).astype(np.float32)
+        b = rng.standard_normal((n, 256)).astype(np.float32)
+        b[0] = a[0]
+        d = engine.paired_dist(torch.from_numpy(a), torch.from_numpy(b)).cpu().numpy()
+        ref = np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).sum(1))
+        assert d.dtype == np.float64 and np.abs(d - ref).max() <= 1e-12 and d[0] == 0.0
+    assert engine.paired_dist(torch.zeros(0, 256), torch.zeros(0, 256)).shape == (0,)
+
+
 def test_cdist_full_size_properties(engine):
     """BASELINE config 5 scale (1e5 x 1e3): checked through size-independent properties."""
     g = torch.Generator(device="cuda").manual_seed(0)

@@ -113,3 +113,37 @@ def test_nomad_loss_module_matches_reference_formula():
     tst = [torch.randn(2, 5, 8) for _ in range(12)] + [torch.randn(2, 4)]
     exp = sum(torch.nn.functional.l1_loss(t, r) for r, t in zip(ref, tst))
     assert torch.allclose(NomadLoss()(ref, tst), exp)
+
+
+def test_csv_writer_is_byte_identical_to_pandas(tmp_path):
+    """nomad_b200_write_scores_csv vs ``DataFrame.round(3)`` + ``to_csv`` (reference nomad.py:113-120, 138-139): same
+    bytes, including rounding ties, exact integers, tiny and huge magnitudes, signed zero, NaN / inf and labels that
+    need quoting."""
+    import pandas as pd
+    from nomad_b200 import _lib
+    rng = np.random.default_rng(11)
+    base = rng.uniform(0.0, 2.0, size=(257, 9))
+    special = np.array([[0.0005, 0.0015, 0.0025, 1.0, 2.0, 1e-5, -1e-5, 123456.7891, 1e17],
+                        [np.nan, np.inf, -np.inf, -0.0, 0.0, 0.9995, 0.28, 1e-4, 5e-4],
+                        [0.1235, 0.1245, 0.3265, 1e16, 12345678.0005, 3.0, 0.001, 0.01, 0.1]])
+    values = np.vstack([special, base])
+    rows = [f"utt_{i}" for i in range(values.shape[0])]
+    rows[1], rows[2], rows[3] = "with,comma", 'with"quote', " lead space"
+    cols = [f"nmr{j}" for j in range(9)]
+    cols[4] = "a,b"
+    for decimals in (3, 0):
+        ref = pd.DataFrame(values, columns=cols).round(decimals)
+        ref["Test File"] = rows
+        ref.set_index("Test File", inplace=True)
+        p_ref, p_got = tmp_path / f"ref{decimals}.csv", tmp_path / f"got{decimals}.csv"
+        ref.reset_index().to_csv(p_ref, index=False)
+        _lib.write_scores_csv(p_got, "Test File", rows, cols, values, decimals=decimals, threads=3)
+        assert p_got.read_bytes() == p_ref.read_bytes()
+    # one-column frame (nomad_avg.csv) and an empty one
+    avg = values[:, 0]
+    ref = pd.DataFrame({"Test File": rows, "NOMAD": avg}).set_index("Test File").round(3)
+    ref.reset_index().to_csv(tmp_path / "a_ref.csv", index=False)
+    _lib.write_scores_csv(tmp_path / "a_got.csv", "Test File", rows, ["NOMAD"], avg)
+    assert (tmp_path / "a_got.csv").read_bytes() == (tmp_path / "a_ref.csv").read_bytes()
+    _lib.write_scores_csv(tmp_path / "e.csv", "Test File", [], ["NOMAD"], np.zeros((0, 1)))
+    assert (tmp_path / "e.csv").read_bytes() == b"Test File,NOMAD\n"
