@@ -44,7 +44,7 @@ int make_plan(const int64_t* off, int B, Plan* p) {
         m.T = T[6];
         m.frame0 = m.row0 / 64;
         m.frames = m.rows0 / 64;
-        m.pos0 = m.frame0 + POS_K * b + POS_K / 2;
+        m.pos0 = m.frame0 + POS_GAP * b + POS_K / 2;
         NB_CHECK(m.T >= 1 && m.T <= m.frames, "internal: frame bookkeeping (T=%d frames=%d)", m.T, m.frames);
         row += m.rows0;
         if (T[0] > max_T0) max_T0 = T[0];
@@ -54,7 +54,7 @@ int make_plan(const int64_t* off, int B, Plan* p) {
     p->total_samples = off[B] - off[0];
     p->rows0 = row;
     p->frames = row / 64;
-    p->pos_rows = p->frames + (long long)POS_K * B + POS_K / 2;
+    p->pos_rows = p->frames + (long long)POS_GAP * B + POS_K / 2;
     p->max_chunks = (max_T0 + STAT_CHUNK - 1) / STAT_CHUNK;
     build_attention_items(*p, &p->attn_items);
     return 0;

@@ -548,7 +548,7 @@ size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
     if (loss_plan(B, N, &p)) return 0;
     const size_t fwd = carve_workspace(p, nullptr, nullptr, true);
     const long long frames_e = p.frames / 2, rows0_e = p.rows0 / 2;
-    const long long pos_rows_e = frames_e + (long long)POS_K * B + POS_K / 2;
+    const long long pos_rows_e = frames_e + (long long)POS_GAP * B + POS_K / 2;
     return fwd + carve_loss(p, B, frames_e, rows0_e, pos_rows_e, with_grad != 0, nullptr, nullptr) + 2048;
 }
 
@@ -575,7 +575,7 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
         p.utt[B + b].wav_off = clean_off + (long long)b * N;
     }
     const long long F = p.frames, Fe = F / 2, R0e = p.rows0 / 2;
-    const long long pos_rows_e = Fe + (long long)POS_K * B + POS_K / 2;
+    const long long pos_rows_e = Fe + (long long)POS_GAP * B + POS_K / 2;
     const int T = p.max_T;
     Workspace ws;
     const size_t fwd_bytes = carve_workspace(p, workspace_dev, &ws, true);

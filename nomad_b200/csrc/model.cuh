@@ -15,6 +15,9 @@ static constexpr int LAYERS = 12;
 static constexpr int POS_K = 128;
 static constexpr int POS_G = 16;
 static constexpr int POS_GC = 48;  // channels per group
+// zero rows between consecutive utterances in the padded positional-conv layout: one gap serves as the right context
+// (63 rows) of the utterance before it and the left context (64 rows) of the one after it
+static constexpr int POS_GAP = 64;
 static constexpr int EMB = 256;
 static constexpr int NSTAT = 65;   // 10 tap sums + 55 tap cross-products of the waveform
 static constexpr int STAT_CHUNK = 4096;  // conv0 frames per wave-stats block
