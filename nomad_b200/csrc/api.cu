@@ -753,9 +753,10 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
              workspace_bytes, core + wav_bytes + emb_bytes);
     float* wav_dev = (float*)((char*)workspace_dev + core);
     float* emb_dev = (float*)((char*)workspace_dev + core + wav_bytes);
-    // H2D in up to 4 utterance groups of about equal size on a side stream; the compute stream picks each group up
-    // as it lands (front end of group g overlaps the copy of group g + 1)
-    static const int max_groups = getenv("NOMAD_B200_H2D_GROUPS") ? atoi(getenv("NOMAD_B200_H2D_GROUPS")) : 4;
+    // H2D in up to 8 utterance groups on a side stream; the compute stream picks each group up as it lands (front end
+    // of group g overlaps the copy of group g + 1).  The first group is half the size of the others so that the
+    // GPU starts computing as early as possible.
+    static const int max_groups = getenv("NOMAD_B200_H2D_GROUPS") ? atoi(getenv("NOMAD_B200_H2D_GROUPS")) : 8;
     FrontPipe pipe;
     if (!h->copy_stream) {
         NB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -768,8 +769,8 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
         pipe.n_groups = G;
         pipe.first[0] = 0;
         int b = 0;
-        for (int g = 1; g < G; ++g) {  // cut where the cumulative sample count passes g / G of the total
-            const long long cut = sample_offsets[0] + total * g / G;
+        for (int g = 1; g < G; ++g) {  // cut where the cumulative sample count passes (2 g - 1) / (2 G) of the total
+            const long long cut = sample_offsets[0] + total * (2 * g - 1) / (2 * G);
             while (b < B - (G - g) && sample_offsets[b + 1] <= cut) ++b;
             if (b <= pipe.first[g - 1]) b = pipe.first[g - 1] + 1;
             pipe.first[g] = b;
