@@ -87,18 +87,24 @@ __device__ __forceinline__ float2 ln_row_stats(const float* part, long long row)
 
 // (mean, rstd) of this thread's row for EPI_LN_FOLD / EPI_RESID_LN.  Called BEFORE the wait for the accumulator so
 // the (L2-latency) loads overlap the mainloop of the tile instead of sitting at the head of its epilogue.
+// EF: the epilogue flags as a compile-time constant (-1 = read them from the arguments).  The hot flag
+// combinations of the scoring path get their own instantiation: no flag tests, no dead paths holding registers.
+template <int EF>
+__device__ __forceinline__ int epi_flags(const GemmEpilogue& e) { return EF >= 0 ? EF : e.flags; }
+
+template <int EF>
 __device__ __forceinline__ float2 epilogue_row_stats(const GemmArgs& args, long long row) {
-    if (row >= args.M || !(args.epi.flags & (EPI_LN_FOLD | EPI_RESID_LN))) return make_float2(0.f, 1.f);
+    if (row >= args.M || !(epi_flags<EF>(args.epi) & (EPI_LN_FOLD | EPI_RESID_LN))) return make_float2(0.f, 1.f);
     return args.epi.ln_part != nullptr ? ln_row_stats(args.epi.ln_part, row)
                                        : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
 }
 
 // FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
-template <bool FULL>
+template <bool FULL, int EF>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
-    const int flags = e.flags;
+    const int flags = epi_flags<EF>(e);
     const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     const long long woff = (row - lane) * e.ldo + col0 + (long long)b * e.out_bstride;  // this warp's first row
     if ((FULL || row_ok) && (flags & EPI_BIAS)) {
@@ -330,7 +336,7 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The accumulator stage is handed back
 // to the MMA warp as soon as the last TMEM load has landed (before that chunk's math and stores).
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
-template <int CHUNKS, bool PAIR, bool CDIST>
+template <int CHUNKS, bool PAIR, bool CDIST, int EF>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src) {
@@ -374,8 +380,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
-            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
-            else epilogue_chunk<false>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
+            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
+            else epilogue_chunk<false, EF>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     rhave = rc.rhave;
@@ -499,10 +505,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const long long row = (long long)m_blk * BM + q * 32 + lane;
-            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
+            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats<-1>(args, row);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<CHUNKS, false, CDIST>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
+            epilogue_tile<CHUNKS, false, CDIST, -1>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
                                          row_st, nullptr, no_prefetch, nullptr);
         }
@@ -537,7 +543,7 @@ struct Pair256 {
     }
 };
 
-template <int NEW, bool CDIST, bool RPF>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
+template <int NEW, bool CDIST, bool RPF, int EF>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     using Cfg = Pair256;
@@ -644,7 +650,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int h = ew >> 2;
         constexpr int HALF = BN / (NEW / 4);  // columns per epilogue warp (two or four column groups)
         // residual prefetch: first 32 x 32 fp32 tile of this warp in tile t (nullptr if it is ragged / absent)
-        const bool want_pf = RPF && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1;
+        const int eflags = epi_flags<EF>(args.epi);
+        const bool want_pf = RPF && (eflags & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1;
         float* rbuf = want_pf ? resid_stage + ew * 1024 : nullptr;
         auto tile_src = [&](int t) -> const float* {
             if (!want_pf || t >= num_tiles) return nullptr;
@@ -669,8 +676,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
-            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats(args, row);
-            if (!CDIST && !want_pf && (args.epi.flags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
+            const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats<EF>(args, row);
+            if (!CDIST && !want_pf && (eflags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
                 // no prefetch buffer (16-warp variant): at least pull the NEXT tile's slice of the fp32 residual
                 // stream into L2 a whole mainloop ahead of its use
                 const int nt = tile + num_pairs;
@@ -683,7 +690,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float* next_src = tile_src(tile + num_pairs);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<HALF / 32, true, CDIST>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+            epilogue_tile<HALF / 32, true, CDIST, EF>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
                                            row_st, rbuf, rhave, next_src);
         }
@@ -859,13 +866,13 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
 }
 
-template <int NEW, bool CDIST, bool RPF = false>
+template <int NEW, bool CDIST, bool RPF = false, int EF = -1>
 static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
     constexpr int SMEM = Cfg::smem_bytes(NEW, RPF);
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -878,7 +885,7 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_pair_kernel<NEW, CDIST, RPF><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
+    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
@@ -896,9 +903,24 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     const int fl = args.epi.flags;
     const bool heavy = args.K <= 1024 && ((fl & (EPI_GELU | EPI_SAVE_DGELU)) != 0 ||
                                           ((fl & (EPI_RESID | EPI_RESID_LN)) != 0 && !(fl & EPI_STATS_OUT)));
-    if (epi16 == 2 || (epi16 == 1 && heavy)) return launch_pair_impl<16, false>(st, A, B, args);
+    // hot flag combinations of the scoring path run flag-specialised instantiations (NOMAD_B200_EPI_SPEC=0: generic)
+    static const int spec = getenv("NOMAD_B200_EPI_SPEC") ? atoi(getenv("NOMAD_B200_EPI_SPEC")) : 1;
+    constexpr int F_FC1 = EPI_LN_FOLD | EPI_GELU | EPI_OUT_H16;
+    constexpr int F_QKV = EPI_LN_FOLD | EPI_OUT_H16;
+    constexpr int F_CONV = EPI_GELU | EPI_OUT_H16;
+    constexpr int F_RES = EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32 | EPI_OUT_H16 | EPI_STATS_OUT;
+    if (epi16 == 2 || (epi16 == 1 && heavy)) {
+        if (spec && fl == F_FC1) return launch_pair_impl<16, false, false, F_FC1>(st, A, B, args);
+        if (spec && fl == F_CONV) return launch_pair_impl<16, false, false, F_CONV>(st, A, B, args);
+        return launch_pair_impl<16, false>(st, A, B, args);
+    }
     static const int rpf = getenv("NOMAD_B200_RESID_PREFETCH") ? atoi(getenv("NOMAD_B200_RESID_PREFETCH")) : 1;
-    if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) return launch_pair_impl<8, false, true>(st, A, B, args);
+    if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) {
+        if (spec && fl == F_RES) return launch_pair_impl<8, false, true, F_RES>(st, A, B, args);
+        return launch_pair_impl<8, false, true>(st, A, B, args);
+    }
+    if (spec && fl == F_QKV) return launch_pair_impl<8, false, false, F_QKV>(st, A, B, args);
+    if (spec && fl == F_CONV) return launch_pair_impl<8, false, false, F_CONV>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
 
