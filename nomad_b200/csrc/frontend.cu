@@ -12,6 +12,9 @@
 
 #include "kernels.cuh"
 
+#ifndef NB_CONV0_BLOCKS
+#define NB_CONV0_BLOCKS 3
+#endif
 #ifndef NB_CONV0_GELU_H2
 #define NB_CONV0_GELU_H2 1
 #endif
@@ -263,7 +266,7 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
+__global__ void __launch_bounds__(256, NB_CONV0_BLOCKS) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
                                                         int B, int blk0, const float* __restrict__ fold,
                                                         const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
     const int blk = blk0 + blockIdx.x;
@@ -279,64 +282,65 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, q = lane & 3;
-    // B fragments + shifts of this warp's 8 channel tiles
-    uint32_t bf[8][2], bl[8][2];
-    float sh[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const int cb = warp * 64 + nt * 8;
-        const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cb + r) * 32);
-        bf[nt][0] = __ldg(h + q);
-        bf[nt][1] = __ldg(h + q + 4);
-        bl[nt][0] = __ldg(h + 8 + q);
-        bl[nt][1] = __ldg(h + 8 + q + 4);
-        sh[nt][0] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q) * 12 + 10);
-        sh[nt][1] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q + 1) * 12 + 10);
-    }
     __syncthreads();
     const int valid = m.T0 - t_base;
-#pragma unroll 1
+    // A fragments of the two k-steps for all four 16-row tiles of the block (32 registers, built once):
+    // a[0], a[1] = K slots 2q, 2q+1 of rows r, r+8; a[2], a[3] = slots 2q+8, 2q+9
+    uint32_t a1[4][4], a2[4][4];
+#pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-        // A fragments of the two k-steps: a[0], a[1] = K slots 2q, 2q+1 of rows r, r+8; a[2], a[3] = slots 2q+8, 2q+9
-        uint32_t a1[4], a2[4];
-        {
-            const int ib[2] = {5 * (mt * 16 + r), 5 * (mt * 16 + r) + 40};  // first sample of rows r and r + 8
+        const int ib[2] = {5 * (mt * 16 + r), 5 * (mt * 16 + r) + 40};  // first sample of rows r and r + 8
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const float* x = xs + ib[k];
-                // step 1, slots 2q, 2q+1: xh[2q], xh[2q+1]
-                a1[k] = pack_op(x[2 * q], x[2 * q + 1]);
-                // step 1, slots 2q+8, 2q+9: q = 0 -> xh[8], xh[9];  q >= 1 -> xl[2q-2], xl[2q-1]
-                {
-                    const int o = q == 0 ? 8 : 2 * q - 2;
-                    const float x0 = x[o], x1 = x[o + 1];
-                    const uint32_t hh = pack_op(x0, x1);
-                    const float2 hf = unpack_op(hh);
-                    a1[2 + k] = q == 0 ? hh : pack_op(x0 - hf.x, x1 - hf.y);
-                }
-                // step 2, slots 2q, 2q+1: q < 2 -> xl[6+2q], xl[7+2q];  q >= 2 -> xh[2q-4], xh[2q-3]
-                {
-                    const int o = q < 2 ? 6 + 2 * q : 2 * q - 4;
-                    const float x0 = x[o], x1 = x[o + 1];
-                    const uint32_t hh = pack_op(x0, x1);
-                    const float2 hf = unpack_op(hh);
-                    a2[k] = q < 2 ? pack_op(x0 - hf.x, x1 - hf.y) : hh;
-                }
-                // step 2, slots 2q+8, 2q+9 = xh[2q+4], xh[2q+5] (q = 3: slots 14, 15 meet zero taps)
-                a2[2 + k] = pack_op(x[2 * q + 4], x[2 * q + 5]);
+        for (int k = 0; k < 2; ++k) {
+            const float* x = xs + ib[k];
+            // step 1, slots 2q, 2q+1: xh[2q], xh[2q+1]
+            a1[mt][k] = pack_op(x[2 * q], x[2 * q + 1]);
+            // step 1, slots 2q+8, 2q+9: q = 0 -> xh[8], xh[9];  q >= 1 -> xl[2q-2], xl[2q-1]
+            {
+                const int o = q == 0 ? 8 : 2 * q - 2;
+                const float x0 = x[o], x1 = x[o + 1];
+                const uint32_t hh = pack_op(x0, x1);
+                const float2 hf = unpack_op(hh);
+                a1[mt][2 + k] = q == 0 ? hh : pack_op(x0 - hf.x, x1 - hf.y);
             }
+            // step 2, slots 2q, 2q+1: q < 2 -> xl[6+2q], xl[7+2q];  q >= 2 -> xh[2q-4], xh[2q-3]
+            {
+                const int o = q < 2 ? 6 + 2 * q : 2 * q - 4;
+                const float x0 = x[o], x1 = x[o + 1];
+                const uint32_t hh = pack_op(x0, x1);
+                const float2 hf = unpack_op(hh);
+                a2[mt][k] = q < 2 ? pack_op(x0 - hf.x, x1 - hf.y) : hh;
+            }
+            // step 2, slots 2q+8, 2q+9 = xh[2q+4], xh[2q+5] (q = 3: slots 14, 15 meet zero taps)
+            a2[mt][2 + k] = pack_op(x[2 * q + 4], x[2 * q + 5]);
         }
-        const int row0 = mt * 16 + r, row1 = row0 + 8;
-        op_t* o0 = out + (long long)(row_base + row0) * CONV_DIM + warp * 64 + 4 * q;
-        op_t* o1 = out + (long long)(row_base + row1) * CONV_DIM + warp * 64 + 4 * q;
+    }
+    op_t* obase = out + (long long)(row_base + r) * CONV_DIM + warp * 64 + 4 * q;
+    const int src = (lane & ~3) | ((2 * q) & 3);
+#pragma unroll 1
+    for (int np = 0; np < 4; ++np) {  // pairs of channel tiles: 16 channels = 32 B per row per quad
+        // B fragments + shifts of the two 8-channel tiles (streamed: they are L1-resident, the A side is not)
+        uint32_t bf[2][2], bl[2][2];
+        float sh[2][2];
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {  // pairs of channel tiles: 16 channels = 32 B per row per quad
-            float c0[4] = {sh[2 * np][0], sh[2 * np][1], sh[2 * np][0], sh[2 * np][1]};
-            float c1[4] = {sh[2 * np + 1][0], sh[2 * np + 1][1], sh[2 * np + 1][0], sh[2 * np + 1][1]};
-            mma_f16_16816(c0, a2, bl[2 * np][0], bl[2 * np][1]);
-            mma_f16_16816(c1, a2, bl[2 * np + 1][0], bl[2 * np + 1][1]);
-            mma_f16_16816(c0, a1, bf[2 * np][0], bf[2 * np][1]);
-            mma_f16_16816(c1, a1, bf[2 * np + 1][0], bf[2 * np + 1][1]);
+        for (int i = 0; i < 2; ++i) {
+            const int cb = warp * 64 + (2 * np + i) * 8;
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cb + r) * 32);
+            bf[i][0] = __ldg(h + q);
+            bf[i][1] = __ldg(h + q + 4);
+            bl[i][0] = __ldg(h + 8 + q);
+            bl[i][1] = __ldg(h + 8 + q + 4);
+            sh[i][0] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q) * 12 + 10);
+            sh[i][1] = __ldg(fold + ((long long)b * CONV_DIM + cb + 2 * q + 1) * 12 + 10);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            float c0[4] = {sh[0][0], sh[0][1], sh[0][0], sh[0][1]};
+            float c1[4] = {sh[1][0], sh[1][1], sh[1][0], sh[1][1]};
+            mma_f16_16816(c0, a2[mt], bl[0][0], bl[0][1]);
+            mma_f16_16816(c1, a2[mt], bl[1][0], bl[1][1]);
+            mma_f16_16816(c0, a1[mt], bf[0][0], bf[0][1]);
+            mma_f16_16816(c1, a1[mt], bf[1][0], bf[1][1]);
             // packed pairs: e = tile 2np (cols 2q, 2q+1), f = tile 2np+1, rows row0 / row1
 #if NB_CONV0_GELU_H2
             uint32_t e0 = gelu_pair_h2(c0[0], c0[1]), e1 = gelu_pair_h2(c0[2], c0[3]);
@@ -346,17 +350,17 @@ __global__ void __launch_bounds__(256, 3) conv0_mma_kernel(const float* __restri
             uint32_t f0 = pack_op(gelu_act(c1[0]), gelu_act(c1[1])), f1 = pack_op(gelu_act(c1[2]), gelu_act(c1[3]));
 #endif
             // lane q stores channels 4q..4q+3 of the 16: q<2 -> from tile 2np lanes (2q, 2q+1); q>=2 -> tile 2np+1
-            const int src = (lane & ~3) | ((2 * q) & 3);
             const uint32_t a_e0 = __shfl_sync(0xffffffffu, e0, src), b_e0 = __shfl_sync(0xffffffffu, e0, src + 1);
             const uint32_t a_f0 = __shfl_sync(0xffffffffu, f0, src), b_f0 = __shfl_sync(0xffffffffu, f0, src + 1);
             const uint32_t a_e1 = __shfl_sync(0xffffffffu, e1, src), b_e1 = __shfl_sync(0xffffffffu, e1, src + 1);
             const uint32_t a_f1 = __shfl_sync(0xffffffffu, f1, src), b_f1 = __shfl_sync(0xffffffffu, f1, src + 1);
             uint2 v0 = q < 2 ? make_uint2(a_e0, b_e0) : make_uint2(a_f0, b_f0);
             uint2 v1 = q < 2 ? make_uint2(a_e1, b_e1) : make_uint2(a_f1, b_f1);
+            const int row0 = mt * 16 + r, row1 = row0 + 8;
             if (row0 >= valid) v0 = make_uint2(0u, 0u);
             if (row1 >= valid) v1 = make_uint2(0u, 0u);
-            *reinterpret_cast<uint2*>(o0 + np * 16) = v0;
-            *reinterpret_cast<uint2*>(o1 + np * 16) = v1;
+            *reinterpret_cast<uint2*>(obase + (long long)(mt * 16) * CONV_DIM + np * 16) = v0;
+            *reinterpret_cast<uint2*>(obase + (long long)(mt * 16 + 8) * CONV_DIM + np * 16) = v1;
         }
     }
 }
