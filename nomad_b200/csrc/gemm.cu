@@ -909,18 +909,28 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     constexpr int F_QKV = EPI_LN_FOLD | EPI_OUT_H16;
     constexpr int F_CONV = EPI_GELU | EPI_OUT_H16;
     constexpr int F_RES = EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32 | EPI_OUT_H16 | EPI_STATS_OUT;
+    // loss path (activations saved for the backward) and the layers at the ends of the stack
+    constexpr int F_FC1_SAVE = EPI_BIAS | EPI_GELU | EPI_OUT_H16 | EPI_SAVE_DGELU;
+    constexpr int F_CONV_SAVE = EPI_GELU | EPI_OUT_H16 | EPI_SAVE_DGELU;
+    constexpr int F_LIN_H16 = EPI_BIAS | EPI_OUT_H16;
+    constexpr int F_RES_PLAIN = EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32;
     if (epi16 == 2 || (epi16 == 1 && heavy)) {
         if (spec && fl == F_FC1) return launch_pair_impl<16, false, false, F_FC1>(st, A, B, args);
         if (spec && fl == F_CONV) return launch_pair_impl<16, false, false, F_CONV>(st, A, B, args);
+        if (spec && fl == F_FC1_SAVE) return launch_pair_impl<16, false, false, F_FC1_SAVE>(st, A, B, args);
+        if (spec && fl == F_CONV_SAVE) return launch_pair_impl<16, false, false, F_CONV_SAVE>(st, A, B, args);
         return launch_pair_impl<16, false>(st, A, B, args);
     }
     static const int rpf = getenv("NOMAD_B200_RESID_PREFETCH") ? atoi(getenv("NOMAD_B200_RESID_PREFETCH")) : 1;
     if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) {
         if (spec && fl == F_RES) return launch_pair_impl<8, false, true, F_RES>(st, A, B, args);
+        if (spec && fl == F_RES_PLAIN) return launch_pair_impl<8, false, true, F_RES_PLAIN>(st, A, B, args);
         return launch_pair_impl<8, false, true>(st, A, B, args);
     }
     if (spec && fl == F_QKV) return launch_pair_impl<8, false, false, F_QKV>(st, A, B, args);
     if (spec && fl == F_CONV) return launch_pair_impl<8, false, false, F_CONV>(st, A, B, args);
+    if (spec && fl == F_CONV_SAVE) return launch_pair_impl<8, false, false, F_CONV_SAVE>(st, A, B, args);
+    if (spec && fl == F_LIN_H16) return launch_pair_impl<8, false, false, F_LIN_H16>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
 
