@@ -368,6 +368,29 @@ def test_mixed_long_short_batch_against_oracle(engine, state_dict):
     np.testing.assert_array_equal(engine.embed_host(flat[: off[2]], off[:3]), engine.embed(waves[:2]).cpu().numpy())
 
 
+def test_extreme_batch_shapes(engine, state_dict):
+    """Shapes at the edges of the batch planner: one 60 s utterance alone (T = 2999, 24 query tiles), a thousand
+    minimum-length utterances (T = 1 each), and a batch mixing both extremes -- against the oracle on a sample."""
+    from oracle import w2v_oracle as O
+    g = torch.Generator().manual_seed(9)
+    long_w = 0.1 * torch.randn(960000, generator=g)
+    e_long = engine.embed([long_w]).cpu().numpy()
+    assert np.isfinite(e_long).all()
+    with torch.no_grad():
+        ref = O.embed(state_dict, long_w[None]).numpy()
+    assert np.abs(e_long - ref).max() <= EMB_TOL
+    tiny = [0.1 * torch.randn(400 + (i % 3), generator=g) for i in range(1000)]
+    e_tiny = engine.embed(tiny).cpu().numpy()
+    assert e_tiny.shape == (1000, 256) and np.isfinite(e_tiny).all()
+    np.testing.assert_allclose(np.linalg.norm(e_tiny, axis=1), 1.0, atol=1e-5)
+    pick = [0, 1, 2, 500, 999]
+    ref = O.embed_each(state_dict, [tiny[i] for i in pick]).numpy()
+    assert np.abs(e_tiny[pick] - ref).max() <= EMB_TOL
+    mixed = engine.embed([tiny[0], long_w, tiny[1]]).cpu().numpy()
+    np.testing.assert_array_equal(mixed[1], e_long[0])
+    np.testing.assert_array_equal(mixed[[0, 2]], e_tiny[[0, 1]])
+
+
 # ------------------------------------------------------------------------------------------- loss
 def _loss_nomad(state_dict, golden_dir, fgm):
     from nomad_b200.nomad import Nomad
