@@ -175,6 +175,7 @@ class Nomad():
         self.feature_grad_mult = float(feature_grad_mult)
         self.max_batch_samples = int(max_batch_seconds * 16000)
         self.device_ingest = os.environ.get("NOMAD_B200_DEVICE_INGEST", "1") != "0"
+        self.window_files = int(os.environ.get("NOMAD_B200_WINDOW_FILES", "4096"))
 
     def predict(self, mode='dir', nmr='data/nmr-data', deg='data/test-data', results_path=None):
         if nmr is None:
@@ -271,32 +272,46 @@ class Nomad():
         return embeddings
 
     def embed_waves(self, waves: Sequence[torch.Tensor]) -> np.ndarray:
-        """Embed variable-length mono waveforms in length-bucketed batches; output order == input order."""
+        """Embed variable-length mono waveforms in length-bucketed batches; output order == input order.
+        Batches are enqueued back to back; the only synchronisation is the single device-to-host copy at the end."""
+        if len(waves) == 0:
+            return np.zeros((0, EMB_DIM), dtype=np.float32)
         lengths = [int(w.numel()) for w in waves]
-        out = np.empty((len(waves), EMB_DIM), dtype=np.float32)
+        out = torch.empty((len(waves), EMB_DIM), dtype=torch.float32, device=self.engine.device)
         for idx in plan_batches(lengths, self.max_batch_samples):
             emb = self.engine.embed([waves[i] for i in idx])
-            out[idx] = emb.cpu().numpy()
-        return out
+            out[torch.as_tensor(idx, device=self.engine.device)] = emb
+        return out.cpu().numpy()
 
     # Function that extract NOMAD embeddings and store them in a DataFrame (nomad.py:166-189)
     def get_embeddings_csv(self, model, file_names, root=False):
+        """Per-file loop of the reference, restructured for throughput: files are read in windows of
+        ``self.window_files`` (bounded memory for 100 k-file corpora), every window is length-bucketed into batches,
+        and the GPU works on window k while the host reads window k + 1 (no per-batch synchronisation)."""
         file_names_arr = np.array(file_names)
-        waves = []
-        for filename_anchor in file_names_arr:
-            if root:
-                filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
-            else:
-                filepath = filename_anchor
-            # 16-bit PCM wavs are converted / mixed / resampled on the GPU (nomad_b200_ingest_pcm16); same result as
-            # the host ``load_processing`` below, which every other format still takes
-            wave = (audio.load_processing_device(self.engine, filepath, trim=False) if self.device_ingest
-                    else self.load_processing(filepath, trim=False))
-            if wave.shape[-1] < MIN_SAMPLES:
-                raise RuntimeError(f"Calculated padded input size per channel: ({wave.shape[-1]}). Kernel size: (10). "
-                                   "Kernel size can't be greater than actual input size")
-            waves.append(wave.reshape(-1))
-        embeddings = self.embed_waves(waves) if waves else np.zeros((0, EMB_DIM), dtype=np.float32)
+        n_files = len(file_names_arr)
+        parts = []
+        for w0 in range(0, n_files, self.window_files):
+            waves = []
+            for filename_anchor in file_names_arr[w0:w0 + self.window_files]:
+                if root:
+                    filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
+                else:
+                    filepath = filename_anchor
+                # 16-bit PCM wavs are converted / mixed / resampled on the GPU (nomad_b200_ingest_pcm16); same result
+                # as the host ``load_processing`` below, which every other format still takes
+                wave = (audio.load_processing_device(self.engine, filepath, trim=False) if self.device_ingest
+                        else self.load_processing(filepath, trim=False))
+                if wave.shape[-1] < MIN_SAMPLES:
+                    raise RuntimeError(f"Calculated padded input size per channel: ({wave.shape[-1]}). Kernel size: (10). "
+                                       "Kernel size can't be greater than actual input size")
+                waves.append(wave.reshape(-1))
+            lengths = [int(w.numel()) for w in waves]
+            dev_out = torch.empty((len(waves), EMB_DIM), dtype=torch.float32, device=self.engine.device)
+            for idx in plan_batches(lengths, self.max_batch_samples):
+                dev_out[torch.as_tensor(idx, device=self.engine.device)] = self.engine.embed([waves[i] for i in idx])
+            parts.append(dev_out)  # still being computed; the host goes on reading the next window
+        embeddings = (torch.cat(parts).cpu().numpy() if parts else np.zeros((0, EMB_DIM), dtype=np.float32))
         embeddings = pd.DataFrame(embeddings)
         df_emb = pd.concat([file_names.reset_index(), embeddings], axis=1).drop('index', axis=1)
         return df_emb

@@ -180,6 +180,11 @@ def test_bundled_wavs_against_reference_predict(engine, golden_dir, tmp_path, st
     df_avg2, df_dm2 = nomad.predict("csv", str(csv_n), str(csv_d), str(out))
     pd.testing.assert_frame_equal(df_avg2, df_avg)
     pd.testing.assert_frame_equal(df_dm2, df_dm)
+    # reading the file list in small windows, or decoding on the host instead of the GPU, changes nothing
+    nomad.window_files = 1
+    pd.testing.assert_frame_equal(nomad.get_embeddings(nmr_dir).set_index("filename"), emb_n)
+    nomad.window_files, nomad.device_ingest = 4096, False
+    pd.testing.assert_frame_equal(nomad.get_embeddings(deg_dir).set_index("filename"), emb_d)
 
 
 def test_model_call_signature_matches_reference(state_dict, golden_dir):
