@@ -32,6 +32,44 @@ def ev_time(fn, reps, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
+def c1(eng):
+    """configs[0]: nomad.predict('dir') on the bundled wavs (2 degraded vs 4 NMR), through the drop-in API; the oracle
+    port of the reference arithmetic on the host cores next to it."""
+    import tempfile
+    import wave
+
+    from nomad_b200.nomad import Nomad
+    from nomad_b200.weights import random_state_dict as rsd
+    from oracle import w2v_oracle as O
+    nmr = os.path.join(ROOT, "tests", "golden", "wavs", "nmr-data")
+    deg = os.path.join(ROOT, "tests", "golden", "wavs", "test-data")
+    sd = rsd(1234)
+    nomad = Nomad(state_dict=sd)
+    with tempfile.TemporaryDirectory() as td:
+        nomad.predict("dir", nmr, deg, td)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            nomad.predict("dir", nmr, deg, td)
+        torch.cuda.synchronize()
+        ours = (time.perf_counter() - t0) / 5
+    waves, secs = [], 0.0
+    for d in (nmr, deg):
+        for f in os.listdir(d):
+            with wave.open(os.path.join(d, f), "rb") as w:
+                pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
+            waves.append(torch.from_numpy(pcm))
+            secs += len(pcm) / 16000.0
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        e = O.embed_each(sd, waves).numpy()
+    O.cdist_mean(e[4:], e[:4])
+    cpu = time.perf_counter() - t0
+    return {"config": "c1: nomad.predict('dir') on the bundled wavs (6 files, %.1f utt-s), wall clock incl. file reads and CSV "
+                      "writes" % secs, "ours_s": ours, "oracle_cpu_s": cpu, "cores": os.cpu_count(), "speedup": cpu / ours}
+
+
 def c3(eng, n_utts=1250):
     """corpus scoring slice: n_utts variable-length (1-20 s) utterances, length-bucketed batches, one GPU.
     (100 k utterances on 8 GPUs = 12.5 k per GPU; this is a 1/10 sample of one GPU's share.)"""
@@ -93,10 +131,10 @@ def c5(eng):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c3", "c4", "c5"]
+    which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
     eng = Engine(random_state_dict(1234), 0)
     for w in which:
         t0 = time.time()
-        r = {"c3": c3, "c4": c4, "c5": c5}[w](eng)
+        r = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](eng)
         r["wall_s"] = time.time() - t0
         print(json.dumps(r), flush=True)
