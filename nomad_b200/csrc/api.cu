@@ -531,14 +531,7 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             NB_TRY(gemm_h16(st, A, Bw, (int)F, 3 * EMBED, EMBED, 1, e, impl));
         }
         if (impl == 0) {
-            static const int attn_sel = getenv("NOMAD_B200_ATTN") ? atoi(getenv("NOMAD_B200_ATTN")) : 0;
-            if (attn_sel == 1) {  // previous generation: one-shot tcgen05 kernel (T <= 256) + streaming mma.sync kernel
-                NB_TRY(launch_attention_tc(st, Lb.qkv, ws.meta, p.B, p.max_T, F, Lb.attn, Lb.lse));
-                if (p.max_T > 256) NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 256));
-            } else {
-                NB_TRY(launch_attention_fa(st, Lb.qkv, ws.attn_items, (int)(p.attn_items.size() / 4), F, Lb.attn,
-                                           Lb.lse));
-            }
+            NB_TRY(launch_attention_fa(st, Lb.qkv, ws.attn_items, (int)(p.attn_items.size() / 4), F, Lb.attn, Lb.lse));
         } else {
             NB_TRY(launch_attention(st, Lb.qkv, ws.meta, p.B, p.max_T, Lb.attn, Lb.lse, 0));
         }

@@ -28,12 +28,9 @@ int launch_pos_finish_ln(cudaStream_t st, const float* x0, const op_t* pos_y, co
 // GEMM epilogue can rebuild the fp32 residual), optional compact copy layer_out[(utt * T + t) * 768 + c]
 int launch_ln768(cudaStream_t st, const float* pre, const UttMeta* meta, int B, long long frames, const float* g,
                  const float* b, float* x, op_t* xh, float* stats, float* layer_out, int layer_T);
-// streaming mma.sync kernel (any T); utterances with T <= skip_T_le are left to the tcgen05 kernel
+// streaming mma.sync kernel (any T): the attention of the SIMT cross-check path (gemm_impl = 1); skip_T_le = 0
 int launch_attention(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, op_t* out, float* lse,
                      int skip_T_le);
-// attention_tc.cu: tcgen05 kernel for utterances with T <= 256 (skips longer ones)
-int launch_attention_tc(cudaStream_t st, const op_t* qkv, const UttMeta* meta, int B, int max_T, long long frames,
-                        op_t* out, float* lse);
 // attention_fa.cu: persistent tcgen05 flash attention over the plan's work list (any T)
 int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items, int n_items,
                         long long frames, op_t* out, float* lse);
