@@ -153,6 +153,11 @@ def run_ours(args):
     from nomad_b200.engine import Engine
     from nomad_b200.weights import load_state_dict
 
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner on the
+    # first collective) goes to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = init_from_env("nccl")
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
@@ -229,6 +234,8 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
 
     utt_s_per_step = CLIPS * CLIP_SECONDS * world
     ms_per_step = total_ms / args.steps
