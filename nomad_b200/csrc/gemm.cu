@@ -65,6 +65,12 @@ struct RowCtx {
     float* rbuf;
     bool rhave;
     const float* rnext;
+    // Column vectors of this warp's column range (bias or c | s or gamma | beta), staged in shared memory once per
+    // tile by epilogue_stage_vectors: the chunk loop then reads them with broadcast LDS instead of one L2 round
+    // trip per chunk (the kernel's 200+ KB of shared memory leave almost no L1).  nullptr = read global memory.
+    const float* vec;
+    int vec_stride;  // floats per staged vector (= columns per epilogue warp)
+    int vec_col0;    // first column of the staged range
 };
 // (mean, rstd) of a 768-wide row from its LN_PARTS partial (mean, M2) pairs of 64 columns each (Chan et al.)
 __device__ __forceinline__ float2 ln_row_stats(const float* part, long long row) {
@@ -99,6 +105,27 @@ __device__ __forceinline__ float2 epilogue_row_stats(const GemmArgs& args, long 
                                        : __ldg(reinterpret_cast<const float2*>(args.epi.ln_stats) + row);
 }
 
+// Stage the column vectors of columns [c0, c0 + W) for one epilogue warp: slot 0 = bias (or fold_c), slot 1 = fold_s
+// (or ln_g), slot 2 = ln_b.  Called once per tile, before the wait for the accumulator.  Only complete ranges are
+// staged (the caller falls back to global loads otherwise).
+template <int EF, int W>
+__device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& e, float* vec, int c0, int lane) {
+    const int flags = epi_flags<EF>(e);
+    __syncwarp();  // the previous tile's chunk loop is done reading
+    if (lane * 4 < W) {
+        if (flags & EPI_BIAS) reinterpret_cast<float4*>(vec)[lane] = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + lane);
+        if (flags & EPI_LN_FOLD) {
+            reinterpret_cast<float4*>(vec)[lane] = __ldg(reinterpret_cast<const float4*>(e.fold_c + c0) + lane);
+            reinterpret_cast<float4*>(vec + W)[lane] = __ldg(reinterpret_cast<const float4*>(e.fold_s + c0) + lane);
+        }
+        if (flags & EPI_RESID_LN) {
+            reinterpret_cast<float4*>(vec + W)[lane] = __ldg(reinterpret_cast<const float4*>(e.ln_g + c0) + lane);
+            reinterpret_cast<float4*>(vec + 2 * W)[lane] = __ldg(reinterpret_cast<const float4*>(e.ln_b + c0) + lane);
+        }
+    }
+    __syncwarp();
+}
+
 // FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
 template <bool FULL, int EF>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
@@ -112,7 +139,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 t = __ldg(bp + j);
+                const float4 t = (FULL && rc.vec) ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j)
+                                                  : __ldg(bp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
         }
@@ -124,7 +152,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 a = __ldg(sp + j), c = __ldg(cp + j);
+                const bool sv = FULL && rc.vec != nullptr;
+                const float4 a = sv ? *reinterpret_cast<const float4*>(rc.vec + rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
+                                    : __ldg(sp + j);
+                const float4 c = sv ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j) : __ldg(cp + j);
                 v[4 * j + 0] = fmaf(rs, fmaf(nm, a.x, v[4 * j + 0]), c.x);
                 v[4 * j + 1] = fmaf(rs, fmaf(nm, a.y, v[4 * j + 1]), c.y);
                 v[4 * j + 2] = fmaf(rs, fmaf(nm, a.z, v[4 * j + 2]), c.z);
@@ -179,7 +210,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 t = rpf ? stage_row_f32(rc.rbuf, lane, j) : __ldg(rp + j), g = __ldg(gp + j), bb = __ldg(bp + j);
+                const bool sv = FULL && rc.vec != nullptr;
+                const float4 t = rpf ? stage_row_f32(rc.rbuf, lane, j) : __ldg(rp + j);
+                const float4 g = sv ? *reinterpret_cast<const float4*>(rc.vec + rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
+                                    : __ldg(gp + j);
+                const float4 bb = sv ? *reinterpret_cast<const float4*>(rc.vec + 2 * rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
+                                     : __ldg(bp + j);
                 v[4 * j + 0] += fmaf((t.x - st.x) * st.y, g.x, bb.x);
                 v[4 * j + 1] += fmaf((t.y - st.x) * st.y, g.y, bb.y);
                 v[4 * j + 2] += fmaf((t.z - st.x) * st.y, g.z, bb.z);
@@ -339,7 +375,8 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 template <int CHUNKS, bool PAIR, bool CDIST, int EF>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
-                                              float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src) {
+                                              float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
+                                              const float* vec = nullptr, int vec_stride = 0) {
     const bool row_ok = row < args.M;
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
@@ -350,6 +387,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
     rc.rbuf = rbuf;
     rc.rhave = rhave;
     rc.rnext = nullptr;
+    rc.vec = vec;
+    rc.vec_stride = vec_stride;
+    rc.vec_col0 = col_first;
 #pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
@@ -538,8 +578,14 @@ struct Pair256 {
     // variant has no room).  It is a separate instantiation so that GEMMs without a residual keep the smaller
     // shared-memory carve-out (and with it 60 KB instead of 28 KB of L1 for their epilogue's vector loads).
     static constexpr int resid_bytes(int epi_warps, bool rpf) { return rpf ? epi_warps * 4096 : 0; }
+    // three staged column vectors per epilogue warp (256 / (warps / 4) columns each)
+    static constexpr int vec_bytes(int epi_warps) { return epi_warps * 3 * (BN / (epi_warps / 4)) * 4; }
+    // the mainloop is insensitive to 4 vs 5 vs 6 stages (measured, profiles/r01_gemm_probe_stages.log): 4 leaves room
+    // for the epilogue buffers and, in the plain 8-warp variant, keeps the 196 KB carve-out (60 KB of L1)
+    static constexpr int stages(int epi_warps, bool rpf) { return 4; }
     static constexpr int smem_bytes(int epi_warps, bool rpf) {
-        return STAGES * STAGE_BYTES + epi_warps * 4096 + resid_bytes(epi_warps, rpf) + 1024 + 256;
+        return stages(epi_warps, rpf) * STAGE_BYTES + epi_warps * 4096 + resid_bytes(epi_warps, rpf) + vec_bytes(epi_warps) +
+               1024 + 256;
     }
 };
 
@@ -547,13 +593,15 @@ template <int NEW, bool CDIST, bool RPF, int EF>  // NEW = epilogue warps (8 or 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
     using Cfg = Pair256;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = Cfg::stages(NEW, RPF);
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
     float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF));
+    float* vec_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF) +
+                                                     Cfg::vec_bytes(NEW));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -688,11 +736,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     prefetch_l2_bulk(args.epi.resid + r2 * args.epi.ldr + c2, HALF * 4);
             }
             const float* next_src = tile_src(tile + num_pairs);
+            // column vectors of this warp's HALF columns -> shared memory (only for complete column ranges, batch 1)
+            float* vec = nullptr;
+            if (!CDIST && args.batch == 1 && n_blk * BN + h * HALF + HALF <= args.N &&
+                (eflags & (EPI_BIAS | EPI_LN_FOLD | EPI_RESID_LN)) != 0) {
+                vec = vec_stage + ew * (3 * HALF);
+                epilogue_stage_vectors<EF, HALF>(args.epi, vec, n_blk * BN + h * HALF, lane);
+            }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             epilogue_tile<HALF / 32, true, CDIST, EF>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                           row_st, rbuf, rhave, next_src);
+                                           row_st, rbuf, rhave, next_src, vec, HALF);
         }
     }
     tc_fence_before();
