@@ -42,9 +42,9 @@ CPU_SAMPLE_CLIPS = 16
 PAIR_N, PAIR_M = 100_000, 1_000
 FALLBACK_PEAK_TFLOPS = 1400.0  # B200_PROFILING.md: sustained ~1.4 PFLOP/s (burst fallback 1590)
 # dram__bytes_read.sum + dram__bytes_write.sum per tensor-core GEMM launch, averaged over the 55 GEMM launches of one
-# step (ncu, profiles/r01_v10_gemm_dram.csv: 31.0 GB per step; the algorithmic operand + result bytes of those
+# step (ncu, profiles/r01_v11_gemm_dram.csv: 31.4 GB per step; the algorithmic operand + result bytes of those
 # launches are 33.7 GB)
-GEMM_DRAM_TRAFFIC_BYTES = 563.7e6
+GEMM_DRAM_TRAFFIC_BYTES = 571.5e6
 
 
 def log(*a):
