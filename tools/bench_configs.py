@@ -70,6 +70,44 @@ def c1(eng):
                       "writes" % secs, "ours_s": ours, "oracle_cpu_s": cpu, "cores": os.cpu_count(), "speedup": cpu / ours}
 
 
+def lib(eng, B=256, N=64000):
+    """the oracle's plain torch ops on the SAME B200 (cuDNN convs, cuBLAS GEMMs, eager attention) -- the
+    "library-kernel Blackwell path" -- on the bench workload, fp32 with TF32 tensor cores and fp16 autocast."""
+    from nomad_b200.weights import random_state_dict as rsd
+    from oracle import w2v_oracle as O
+    sd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in rsd(1234).items()}
+    g = torch.Generator().manual_seed(0)
+    wav = (0.1 * torch.randn(B, N, generator=g)).cuda()
+    out = {"config": "lib: oracle torch ops on cuda:0 (cuDNN / cuBLAS eager), %d x %.0f s" % (B, N / 16000)}
+    ref = None
+    for name, tf32, amp in (("fp32_tf32", True, False), ("fp16_autocast", True, True), ("fp32_ieee", False, False)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+
+        def run():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                return O.embed(sd, wav)
+        try:
+            ms = ev_time(run, 3, warm=2)
+            e = run().float()
+            if name == "fp32_ieee":
+                ref = e
+            out[name] = {"ms": ms, "utt_s_per_s": B * N / 16000 / (ms / 1e3), "tflops": B * flops_embed(N) / (ms / 1e3) / 1e12}
+            out[name + "_emb"] = e.cpu()
+        except Exception as ex:  # e.g. out of memory at this batch size
+            out[name] = {"error": str(ex)[:200]}
+    if ref is not None:
+        for name in ("fp32_tf32", "fp16_autocast"):
+            if name + "_emb" in out:
+                out[name]["max_abs_err_vs_fp32"] = float((out[name + "_emb"].cuda() - ref).abs().max())
+    ours = eng.embed_packed(wav.reshape(-1), np.arange(B + 1, dtype=np.int64) * N)
+    if ref is not None:
+        out["nomad_b200_max_abs_err_vs_fp32"] = float((ours - ref).abs().max())
+    for k in [k for k in out if k.endswith("_emb")]:
+        del out[k]
+    return out
+
+
 def c3(eng, n_utts=1250):
     """corpus scoring slice: n_utts variable-length (1-20 s) utterances, length-bucketed batches, one GPU.
     (100 k utterances on 8 GPUs = 12.5 k per GPU; this is a 1/10 sample of one GPU's share.)"""
@@ -135,6 +173,6 @@ if __name__ == "__main__":
     eng = Engine(random_state_dict(1234), 0)
     for w in which:
         t0 = time.time()
-        r = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](eng)
+        r = {"c1": c1, "lib": lib, "c3": c3, "c4": c4, "c5": c5}[w](eng)
         r["wall_s"] = time.time() - t0
         print(json.dumps(r), flush=True)
