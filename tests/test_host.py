@@ -147,3 +147,27 @@ def test_csv_writer_is_byte_identical_to_pandas(tmp_path):
     assert (tmp_path / "a_got.csv").read_bytes() == (tmp_path / "a_ref.csv").read_bytes()
     _lib.write_scores_csv(tmp_path / "e.csv", "Test File", [], ["NOMAD"], np.zeros((0, 1)))
     assert (tmp_path / "e.csv").read_bytes() == b"Test File,NOMAD\n"
+
+
+def test_csv_writer_fuzz_against_pandas(tmp_path):
+    """Random magnitudes (1e-9 .. 1e19, both signs), every rounding setting the reference could plausibly use, and no
+    rounding at all (full shortest-repr digits): the bytes still equal pandas'."""
+    import pandas as pd
+    from nomad_b200 import _lib
+    rng = np.random.default_rng(123)
+    mant = rng.uniform(-10.0, 10.0, size=(400, 7))
+    expo = rng.integers(-9, 19, size=(400, 7))
+    values = mant * (10.0 ** expo)
+    values[::13, 3] = np.round(values[::13, 3])          # exact integers
+    values[::17, 5] = rng.integers(-5, 5, size=values[::17, 5].shape) / 8.0  # exact binary fractions (rounding ties)
+    rows = [f"r{i}" for i in range(values.shape[0])]
+    cols = [f"c{j}" for j in range(values.shape[1])]
+    for decimals in (0, 1, 3, 6, -1):
+        ref = pd.DataFrame(values, columns=cols)
+        if decimals >= 0:
+            ref = ref.round(decimals)
+        ref.insert(0, "Test File", rows)
+        p_ref, p_got = tmp_path / f"ref{decimals}.csv", tmp_path / f"got{decimals}.csv"
+        ref.to_csv(p_ref, index=False)
+        _lib.write_scores_csv(p_got, "Test File", rows, cols, values, decimals=decimals, threads=2)
+        assert p_got.read_bytes() == p_ref.read_bytes(), decimals
