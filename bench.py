@@ -1,21 +1,34 @@
 #!/usr/bin/env python
-"""Benchmark of the NOMAD embedding hot path on B200 (BASELINE.json configs[1]:
-"batch embedding: 256 x 4 s synthetic 16 kHz clips, wav2vec2-base NOMAD head").
+"""Benchmark of the NOMAD scoring hot path on B200 (BASELINE.json configs[1]: "batch embedding: 256 x 4 s synthetic
+16 kHz clips, wav2vec2-base NOMAD head"), with the scoring tail (distance rows against a resident 1 k NMR set).
 
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU arithmetic (oracle port)
+    python bench.py --impl library ...                       # the reference's arithmetic as torch library kernels
+                                                             # (cuDNN / cuBLAS TF32 + SDPA) on the same B200
 
-One "step" = one pass of the hot path (waveform -> 256-d NOMAD embedding) over one batch of 256 synthetic
-4-second clips per GPU.  N > 1 (torchrun): utterances shard across ranks with no data-path collective
-(weak scaling: every rank embeds its own 256-clip batch).  Rank 0 prints ONE JSON line.
+One "step" (every N) = one pass of the hot path over one batch per GPU: 256 synthetic 4-second clips -> wav2vec 2.0
+base -> NOMAD embedding -> distance rows + row means against the (M, 256) NMR embeddings resident on every rank
+(``nomad_b200_score``).  With N > 1 (torchrun, one process per GPU, NCCL) the step ends with the path's exchange:
+every rank sends its row means and matrix rows to rank 0 (point-to-point in the NCCL communicator, exact sizes; the
+matrix is never all-gathered).  Per-GPU work is fixed as N grows ("weak").  The NMR set is embedded sharded and
+all-gathered ONCE before the timed region (that is when `Nomad.predict` does it); its time is reported separately.
 
-* ``value``  : utterance-seconds embedded per second, waveforms already resident in HBM, CUDA-event timed.
-* ``e2e``    : same metric through ``nomad_b200_embed_host`` with pinned HOST buffers (H2D of the waveforms
-               and D2H of the embeddings inside the timed region).
-* ``roofline``: the dominant kernel (tcgen05 GEMM) timed in situ with one CUDA-event pair per launch on the
-               launching stream during the timed region; achieved = sum(2MNK) / sum(duration), against the
-               measured sustained fp16/bf16 tensor peak in MEASURED_PEAKS.json.
-* ``cpu_baseline``: the oracle (torch CPU fp32 restatement of the reference arithmetic) on a bounded sample.
+Rank 0 prints ONE JSON line:
+
+* ``value``   : utterance-seconds embedded per second, whole job, waveforms resident in HBM, CUDA-event timed, max over
+                ranks.
+* ``e2e``     : same step through ``nomad_b200_score_host`` with pinned HOST buffers: H2D of the waveforms, D2H of
+                embeddings + matrix rows + means inside the timed region (row-sharded host results per rank).
+* ``roofline``: the dominant kernel class (tcgen05 GEMM) timed in situ with one CUDA-event pair per launch on the
+                launching stream; achieved = sum(2MNK) / sum(duration), against the measured sustained tensor peak.
+* ``sharded_c3`` : BASELINE configs[2] as a FIXED global workload (strong scaling): C3_DEG variable-length (1-20 s)
+                degraded utterances vs C3_NMR NMR utterances through ``nomad_b200.dist.score_sharded`` -- LPT shard ->
+                embed NMR shard -> NCCL all-gather -> embed degraded shard -> row-slice cdist + means -> rows to rank 0.
+* ``pairwise``: BASELINE configs[4] slice, fixed global PAIR_N x PAIR_M (strong scaling): rows sharded, means to rank 0.
+* ``loss``    : BASELINE configs[3] (N = 1 only; the loss lives inside a user's training step: replicas).
+* ``cpu_baseline`` / ``parity``: the oracle on the host cores over a bounded sample of the same batch, and the achieved
+                embedding error of this library against it on those clips.
 """
 from __future__ import annotations
 
@@ -37,14 +50,20 @@ UNIT = "utt-s/s"
 CLIPS = 256
 CLIP_SECONDS = 4
 SR = 16000
-WORKLOAD = "configs[1]: batch embedding, 256 x 4 s synthetic 16 kHz clips, wav2vec2-base + NOMAD head"
+NMR_M = 1000
+WORKLOAD = ("configs[1]: batch embedding, 256 x 4 s synthetic 16 kHz clips, wav2vec2-base + NOMAD head, scored against "
+            "1000 resident NMR embeddings")
 CPU_SAMPLE_CLIPS = 16
-PAIR_N, PAIR_M = 100_000, 1_000
+C3_DEG, C3_NMR = 4096, NMR_M          # fixed global workload of the strong-scaling leg
+PAIR_N, PAIR_M = 800_000, NMR_M       # fixed global workload of the pairwise leg (1e5 x 1e3 per GPU at N = 8)
+LOSS_B, LOSS_SECONDS = 32, 2
 FALLBACK_PEAK_TFLOPS = 1400.0  # B200_PROFILING.md: sustained ~1.4 PFLOP/s (burst fallback 1590)
-# dram__bytes_read.sum + dram__bytes_write.sum per tensor-core GEMM launch, averaged over the 55 GEMM launches of one
-# step (ncu, profiles/r01_v11_gemm_dram.csv: 31.4 GB per step; the algorithmic operand + result bytes of those
-# launches are 33.7 GB)
+FALLBACK_HBM_GBS = 6500.0
+# dram__bytes_read.sum + dram__bytes_write.sum per tensor-core GEMM launch, averaged over the GEMM launches of one
+# step, from the ncu pass named in TRAFFIC_SOURCE (not measured in this run; the algorithmic operand + result bytes of
+# those launches are 33.7 GB per step)
 GEMM_DRAM_TRAFFIC_BYTES = 571.5e6
+TRAFFIC_SOURCE = "ncu profile profiles/r01_v11_gemm_dram.csv (31.4 GB over the 55 GEMM launches of one step)"
 
 
 def log(*a):
@@ -55,6 +74,17 @@ def synth_batch(clips: int, seed: int):
     import torch
     g = torch.Generator().manual_seed(seed)
     return 0.1 * torch.randn(clips, CLIP_SECONDS * SR, generator=g)
+
+
+def shared_config(weights: str):
+    """The SAME dict in every arm (ours / reference / library), so the driver's same_config check can hold."""
+    return {"workload": WORKLOAD, "clips_per_gpu_per_step": CLIPS, "clip_seconds": CLIP_SECONDS, "frames_per_clip": 199,
+            "nmr_embeddings": NMR_M, "weights": weights,
+            "parallelism": "dp over utterances (one 256-clip batch per GPU); NMR embeddings all-gathered once (NCCL) before "
+                           "the timed region; per step every rank sends its row means + matrix rows to rank 0",
+            "l2": "per-step working set ~6 GB of activations >> 126 MB L2 (inputs larger than L2, no explicit flush)",
+            "reference_arm": f"CPU arms time a bounded sample of this workload per step ({CPU_SAMPLE_CLIPS} of the {CLIPS} "
+                             "clips, same seed) and report the same per-utterance-second metric"}
 
 
 class ClockSampler:
@@ -98,7 +128,8 @@ class ClockSampler:
 
 
 def cpu_reference_rate(steps: int, warmup: int, min_seconds: float = 0.0):
-    """Oracle port on the host cores: `steps` passes over CPU_SAMPLE_CLIPS x 4 s clips.  -> (utt-s/s, ms/step, cores)"""
+    """Oracle port on the host cores: `steps` passes over the first CPU_SAMPLE_CLIPS clips of rank 0's batch, each
+    followed by the scoring tail.  -> (utt-s/s, ms/step, cores, passes, embeddings of the sample)"""
     import torch
 
     from nomad_b200.weights import random_state_dict
@@ -106,7 +137,10 @@ def cpu_reference_rate(steps: int, warmup: int, min_seconds: float = 0.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = random_state_dict(1234)
-    wav = synth_batch(CPU_SAMPLE_CLIPS, 0)
+    wav = synth_batch(CLIPS, 0)[:CPU_SAMPLE_CLIPS].contiguous()
+    g = torch.Generator().manual_seed(4242)
+    nmr = torch.nn.functional.normalize(torch.randn(NMR_M, 256, generator=g), dim=1).numpy()
+    emb = None
     with torch.no_grad():
         for _ in range(warmup):
             O.embed(sd, wav)
@@ -115,11 +149,12 @@ def cpu_reference_rate(steps: int, warmup: int, min_seconds: float = 0.0):
         i = 0
         while i < steps or (time.perf_counter() - t_all) < min_seconds:
             t0 = time.perf_counter()
-            O.embed(sd, wav)
+            emb = O.embed(sd, wav)
+            O.cdist_mean(emb.numpy(), nmr)
             times.append(time.perf_counter() - t0)
             i += 1
     sec = sum(times) / len(times)
-    return CPU_SAMPLE_CLIPS * CLIP_SECONDS / sec, sec * 1e3, cores, len(times)
+    return CPU_SAMPLE_CLIPS * CLIP_SECONDS / sec, sec * 1e3, cores, len(times), emb
 
 
 def run_reference(args):
@@ -127,15 +162,15 @@ def run_reference(args):
     if rank != 0:
         return 0
     steps = max(1, args.steps)
-    rate, ms, cores, n = cpu_reference_rate(steps, min(args.warmup, 1))
-    sample = (f"{CPU_SAMPLE_CLIPS} x {CLIP_SECONDS} s clips per step (1/16 of the 256-clip batch), oracle port of the "
-              f"reference's torch-CPU fp32 path, {cores} threads")
+    rate, ms, cores, n, _ = cpu_reference_rate(steps, min(args.warmup, 1))
+    sample = (f"{CPU_SAMPLE_CLIPS} x {CLIP_SECONDS} s clips per step (1/16 of the 256-clip batch, same seed) + their distance "
+              f"rows against {NMR_M} NMR embeddings; oracle port of the reference's torch-CPU fp32 path (the reference itself "
+              f"needs fairseq, absent here), {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_step": CPU_SAMPLE_CLIPS, "clip_seconds": CLIP_SECONDS,
-                   "weights": "random-init(seed=1234)"},
+        "config": shared_config("random-init(seed=1234)"),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -143,22 +178,128 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# library arm: the reference's arithmetic dispatched to the vendor libraries on the same GPU ("the
+# existing Blackwell path" -- cuDNN convs, cuBLAS TF32 GEMMs, fused SDPA attention).  Plain torch ops, none of this
+# repo's kernels.
+def library_embed(sd, wav):
+    import torch
+    import torch.nn.functional as F
+    P = "ssl_model."
+    x = wav.unsqueeze(1)
+    for i, (k, s) in enumerate(zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2))):
+        x = F.conv1d(x, sd[P + f"feature_extractor.conv_layers.{i}.0.weight"], stride=s)
+        if i == 0:
+            x = F.group_norm(x, 512, sd[P + "feature_extractor.conv_layers.0.2.weight"],
+                             sd[P + "feature_extractor.conv_layers.0.2.bias"], eps=1e-5)
+        x = F.gelu(x)
+    x = x.transpose(1, 2)
+    x = F.layer_norm(x, (512,), sd[P + "layer_norm.weight"], sd[P + "layer_norm.bias"], 1e-5)
+    x = F.linear(x, sd[P + "post_extract_proj.weight"], sd[P + "post_extract_proj.bias"])
+    B, T, Cc = x.shape
+    pc = F.conv1d(x.transpose(1, 2), sd["_pos_w"], sd[P + "encoder.pos_conv.0.bias"], padding=64, groups=16)[..., :T]
+    x = x + F.gelu(pc).transpose(1, 2)
+    x = F.layer_norm(x, (Cc,), sd[P + "encoder.layer_norm.weight"], sd[P + "encoder.layer_norm.bias"], 1e-5)
+    for l in range(12):
+        q_ = P + f"encoder.layers.{l}."
+        lin = lambda t, n: F.linear(t, sd[q_ + n + ".weight"], sd[q_ + n + ".bias"])
+        q = lin(x, "self_attn.q_proj").view(B, T, 12, 64).transpose(1, 2)
+        k = lin(x, "self_attn.k_proj").view(B, T, 12, 64).transpose(1, 2)
+        v = lin(x, "self_attn.v_proj").view(B, T, 12, 64).transpose(1, 2)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, Cc)
+        x = F.layer_norm(x + lin(a, "self_attn.out_proj"), (Cc,), sd[q_ + "self_attn_layer_norm.weight"],
+                         sd[q_ + "self_attn_layer_norm.bias"], 1e-5)
+        h = lin(F.gelu(lin(x, "fc1")), "fc2")
+        x = F.layer_norm(x + h, (Cc,), sd[q_ + "final_layer_norm.weight"], sd[q_ + "final_layer_norm.bias"], 1e-5)
+    e = F.linear(F.relu(x.mean(1)), sd["embedding_layer.1.weight"], sd["embedding_layer.1.bias"])
+    return F.normalize(e, dim=1)
+
+
+def run_library(args):
+    import torch
+
+    from nomad_b200.weights import fold_pos_conv_weight, random_state_dict
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    dev = torch.device("cuda", 0)
+    sd_cpu = random_state_dict(1234)
+    sd = {k: v.to(dev) for k, v in sd_cpu.items()}
+    sd["_pos_w"] = fold_pos_conv_weight(sd_cpu).to(dev)
+    wav_pin = synth_batch(CLIPS, 0).pin_memory()
+    wav_dev = wav_pin.to(dev)
+    g = torch.Generator().manual_seed(4242)
+    nmr = torch.nn.functional.normalize(torch.randn(NMR_M, 256, generator=g), dim=1).to(dev)
+    emb_pin = torch.empty((CLIPS, 256)).pin_memory()
+    dm_pin = torch.empty((CLIPS, NMR_M)).pin_memory()
+
+    def step_dev():
+        with torch.no_grad():
+            e = library_embed(sd, wav_dev)
+            d = torch.cdist(e, nmr)
+            return e, d, d.mean(1)
+
+    def step_host():
+        with torch.no_grad():
+            w = wav_pin.to(dev, non_blocking=True)
+            e = library_embed(sd, w)
+            d = torch.cdist(e, nmr)
+            emb_pin.copy_(e, non_blocking=True)
+            dm_pin.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    step_host()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    ms = timed(step_dev, args.steps)
+    e2e_ms = timed(step_host, args.steps)
+    clocks = sampler.stop()
+    utt_s = CLIPS * CLIP_SECONDS
+    line = {"impl": "library", "metric": METRIC, "value": utt_s / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic", "config": shared_config("random-init(seed=1234)"),
+            "library": "torch eager on cuda:0: cuDNN conv1d, cuBLAS TF32 linears, fused scaled_dot_product_attention, "
+                       "torch.cdist; fp32 storage",
+            "e2e": {"value": utt_s / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(CLIPS * CLIP_SECONDS * SR * 4),
+                    "d2h_bytes_per_step": int(CLIPS * 256 * 4 + CLIPS * NMR_M * 4)},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from nomad_b200 import _lib
-    from nomad_b200.dist import init_from_env
+    from nomad_b200 import dist as nd
     from nomad_b200.engine import Engine
-    from nomad_b200.weights import load_state_dict
+    from nomad_b200.nomad import plan_batches
+    from nomad_b200.weights import flops_embed, load_state_dict
 
     # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner on the
     # first collective) goes to stderr instead
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    rank, world, local = init_from_env("nccl")
+    rank, world, local = nd.init_from_env("nccl")
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     torch.cuda.set_device(local)
@@ -166,16 +307,6 @@ def run_ours(args):
     sd, source = load_state_dict(None, 1234)
     eng = Engine(sd, local)
     lib = _lib.load()
-
-    N = CLIP_SECONDS * SR
-    wav_cpu = synth_batch(CLIPS, seed=rank)
-    off = np.arange(CLIPS + 1, dtype=np.int64) * N
-    wav_dev = wav_cpu.reshape(-1).to(dev)
-    out = torch.empty((CLIPS, 256), dtype=torch.float32, device=dev)
-    wav_pin = wav_cpu.reshape(-1).pin_memory()
-    wav_pin_np = wav_pin.numpy()
-    emb_pin = torch.empty((CLIPS, 256), dtype=torch.float32).pin_memory()
-    emb_pin_np = emb_pin.numpy()
 
     def barrier():
         if world > 1:
@@ -196,8 +327,74 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    step_dev = lambda: eng.embed_packed(wav_dev, off, out)
-    step_host = lambda: eng.embed_host(wav_pin_np, off, emb_pin_np)
+    # ------------------------------------------------------------------ configs[2] slice: fixed global workload, sharded
+    # every rank derives the same lengths; utterance i's samples are a slice of a shared noise bank (content does not
+    # change the arithmetic performed; identical on every N so the scores can be compared across N)
+    rng = np.random.default_rng(0)
+    deg_len = (SR * rng.uniform(1.0, 20.0, size=C3_DEG)).astype(np.int64)
+    nmr_len = (SR * rng.uniform(1.0, 20.0, size=C3_NMR)).astype(np.int64)
+    bank = (0.1 * torch.randn(64, 20 * SR, generator=torch.Generator().manual_seed(99))).to(dev)
+    max_batch_samples = 2000 * SR
+
+    def embed_from_bank(lengths, salt):
+        def fn(idx):
+            out = torch.empty((len(idx), 256), dtype=torch.float32, device=dev)
+            lens = [int(lengths[i]) for i in idx]
+            for b in plan_batches(lens, max_batch_samples):
+                wav = torch.cat([bank[(idx[j] + salt) % 64, : lens[j]] for j in b])
+                off = Engine.offsets([lens[j] for j in b])
+                out[torch.as_tensor(b, device=dev)] = eng.embed_packed(wav, off)
+            return out
+        return fn
+
+    cdist_fn = lambda a, b, wm: eng.cdist_mean(a, b, wm)
+    c3_res = {}
+
+    def c3_pass():
+        res = nd.score_sharded(nmr_len.tolist(), embed_from_bank(nmr_len, 7), deg_len.tolist(), embed_from_bank(deg_len, 0),
+                               cdist_fn, dev, matrix="root")
+        c3_res.update(res)
+        if rank == 0:  # the consumer reads the means on the host (D2H inside the timed region)
+            c3_res["mean_host"] = res["mean"].cpu()
+
+    c3_pass()  # warm-up (NCCL communicators, workspaces)
+    c3_ms = timed(c3_pass, 2) / 2
+    nmr_emb = c3_res["nmr"].contiguous()  # (C3_NMR, 256) on every rank, listing order: the resident NMR set below
+    c3_utt_s = float(deg_len.sum() + nmr_len.sum()) / SR
+    c3_flops = float(sum(flops_embed(int(n)) for n in deg_len) + sum(flops_embed(int(n)) for n in nmr_len))
+    c3_check = float(c3_res["mean_host"].double().mean()) if rank == 0 else None
+    # the exchange on its own: all-gather of the NMR shards, and the rows-to-root transfer of one step
+    nmr_shards = nd.shard_by_cost(nmr_len.tolist(), world)
+    local_nmr = nmr_emb[torch.as_tensor(nmr_shards[rank], device=dev)].contiguous()
+    for _ in range(3):
+        nd.all_gather_shards(local_nmr, nmr_shards)
+    allgather_ms = timed(lambda: nd.all_gather_shards(local_nmr, nmr_shards), 20) / 20
+
+    # ------------------------------------------------------------------ primary: configs[1] batch per GPU + scoring tail
+    N = CLIP_SECONDS * SR
+    wav_cpu = synth_batch(CLIPS, seed=rank)
+    off = np.arange(CLIPS + 1, dtype=np.int64) * N
+    wav_dev = wav_cpu.reshape(-1).to(dev)
+    wav_pin = wav_cpu.reshape(-1).pin_memory()
+    wav_pin_np = wav_pin.numpy()
+    emb_pin = torch.empty((CLIPS, 256), dtype=torch.float32).pin_memory()
+    dm_pin = torch.empty((CLIPS, NMR_M), dtype=torch.float32).pin_memory()
+    mean_pin = torch.empty((CLIPS,), dtype=torch.float64).pin_memory()
+    emb_pin_np, dm_pin_np, mean_pin_np = emb_pin.numpy(), dm_pin.numpy(), mean_pin.numpy()
+    row_shards = [list(range(r * CLIPS, (r + 1) * CLIPS)) for r in range(world)]
+    last = {}
+
+    def step_dev():
+        emb, dm, mean = eng.score_packed(wav_dev, off, nmr_emb)
+        if world > 1:  # the path's exchange: this rank's rows of the result go to rank 0
+            last["mean"] = nd.gather_shards_to_root(mean.reshape(-1, 1), row_shards)
+            last["dm"] = nd.gather_shards_to_root(dm, row_shards)
+        else:
+            last["mean"], last["dm"] = mean, dm
+        last["emb"] = emb
+
+    def step_host():
+        eng.score_host(wav_pin_np, off, nmr_emb, emb_pin_np, dm_pin_np, mean_pin_np)
 
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -219,16 +416,52 @@ def run_ours(args):
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_int64()
     lib.nomad_b200_profile_gemm_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
     lib.nomad_b200_profile_gemm(0)
-    # second named quantity of BASELINE.json's metric: pairwise distances per second (config 4 shape per GPU:
-    # 100 k degraded x 1 k NMR embeddings resident in HBM, matrix materialised + fp64 row means)
-    gq = torch.Generator().manual_seed(100 + rank)
-    deg_e = torch.nn.functional.normalize(torch.randn(PAIR_N, 256, generator=gq), dim=1).to(dev)
-    nmr_e = torch.nn.functional.normalize(torch.randn(PAIR_M, 256, generator=gq), dim=1).to(dev)
-    for _ in range(3):
-        eng.cdist_mean(deg_e, nmr_e)
-    pair_ms = timed(lambda: eng.cdist_mean(deg_e, nmr_e), 20) / 20
-    pair_mean_ms = timed(lambda: eng.cdist_mean(deg_e, nmr_e, want_matrix=False), 20) / 20
     clocks = sampler.stop() if rank == 0 else None
+    exchange_ms = None
+    if world > 1:
+        emb, dm, mean = eng.score_packed(wav_dev, off, nmr_emb)
+
+        def xchg():
+            nd.gather_shards_to_root(mean.reshape(-1, 1), row_shards)
+            nd.gather_shards_to_root(dm, row_shards)
+        exchange_ms = timed(xchg, 20) / 20
+
+    # ------------------------------------------------------------------ configs[4] slice: fixed global PAIR_N x PAIR_M
+    pair_shards = [list(range(r * PAIR_N // world, (r + 1) * PAIR_N // world)) for r in range(world)]
+    n_loc = len(pair_shards[rank])
+    gq = torch.Generator().manual_seed(100 + rank)
+    deg_e = torch.nn.functional.normalize(torch.randn(n_loc, 256, generator=gq), dim=1).to(dev)
+    nmr_e = torch.nn.functional.normalize(torch.randn(PAIR_M, 256, generator=torch.Generator().manual_seed(5)), dim=1).to(dev)
+
+    def pair_step(want_matrix):
+        def fn():
+            _dm, mean = eng.cdist_mean(deg_e, nmr_e, want_matrix=want_matrix)   # matrix rows stay with the rank
+            nd.gather_shards_to_root(mean.reshape(-1, 1), pair_shards)           # means to rank 0
+        return fn
+    for _ in range(3):
+        pair_step(True)()
+    pair_ms = timed(pair_step(True), 10) / 10
+    pair_mean_ms = timed(pair_step(False), 10) / 10
+    del deg_e
+
+    # ------------------------------------------------------------------ configs[3]: loss fwd + bwd (single GPU by nature)
+    loss = None
+    if world == 1:
+        gl = torch.Generator().manual_seed(11)
+        est = (0.1 * torch.randn(LOSS_B, LOSS_SECONDS * SR, generator=gl)).to(dev)
+        cln = (0.1 * torch.randn(LOSS_B, LOSS_SECONDS * SR, generator=gl)).to(dev)
+        hw = 0.03 * torch.randn(256, 768, generator=gl)
+        eng.set_loss_head(hw, torch.zeros(256))
+        for _ in range(3):
+            eng.loss_fwd_bwd(est, cln, 0.1)
+        n1 = eng.launch_count()
+        loss_ms = timed(lambda: eng.loss_fwd_bwd(est, cln, 0.1), 10) / 10
+        loss_launches = (eng.launch_count() - n1) // 10
+        loss_flops = 3.0 * LOSS_B * flops_embed(LOSS_SECONDS * SR)
+        loss = {"workload": f"configs[3]: NOMAD loss fwd+bwd, {LOSS_B} x {LOSS_SECONDS} s estimate/clean pairs, "
+                            "feature_grad_mult 0.1", "ms_per_step": loss_ms, "pairs_per_s": LOSS_B / (loss_ms / 1e3),
+                "tflops_algorithmic": loss_flops / (loss_ms / 1e3) / 1e12, "launches_per_step": int(loss_launches),
+                "flops_definition": "fwd(clean) + fwd(est) + dgrad(est) = 3 * B * F(N); weight gradients excluded"}
 
     if rank != 0:
         if world > 1:
@@ -242,48 +475,69 @@ def run_ours(args):
     value = utt_s_per_step / (ms_per_step / 1e3)
     e2e_value = utt_s_per_step / (e2e_ms / args.steps / 1e3)
 
+    peaks = {}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
-        peak = float(json.load(open(peaks_path)).get("bf16_tflops_sustained", FALLBACK_PEAK_TFLOPS))
+        peaks = json.load(open(peaks_path))
+    if "bf16_tflops_sustained" in peaks:
+        peak = float(peaks["bf16_tflops_sustained"])
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
     else:
         peak, peak_src = FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md sustained figure)"
+    hbm = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
     achieved = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
-
-    from nomad_b200.weights import flops_embed
     step_flops = CLIPS * flops_embed(N)
-    # CPU baseline: rank 0, single-GPU runs only (a reported baseline, not the target)
-    cpu = None
-    if world == 1:
-        cpu_rate, cpu_ms, cores, cpu_n = cpu_reference_rate(1, 1, min_seconds=10.0)
-        cpu = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cpu_n} pass(es) over {CPU_SAMPLE_CLIPS} x {CLIP_SECONDS} s clips (1/16 of the batch), "
-                         f"oracle torch-CPU fp32, {cores} threads, {cpu_ms:.0f} ms/pass"}
 
+    # CPU baseline + achieved parity: rank 0, single-GPU runs only (a reported baseline, not the target)
+    cpu, parity = None, None
+    if world == 1:
+        cpu_rate, cpu_ms, cores, cpu_n, ref_emb = cpu_reference_rate(1, 1, min_seconds=10.0)
+        cpu = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cpu_n} pass(es) over the first {CPU_SAMPLE_CLIPS} x {CLIP_SECONDS} s clips of the batch (1/16) + "
+                         f"their distance rows vs {NMR_M} NMR embeddings, oracle torch-CPU fp32, {cores} threads, "
+                         f"{cpu_ms:.0f} ms/pass"}
+        err = float((last["emb"][:CPU_SAMPLE_CLIPS].cpu() - ref_emb).abs().max())
+        parity = {"emb_max_abs_err_vs_oracle_fp32": err, "clips_compared": CPU_SAMPLE_CLIPS, "tolerance": 1e-3,
+                  "note": "fp16 operands / fp32 accumulate class of north_star (<= 1e-3); checked again in tests/"}
+
+    pair_total = float(PAIR_N) * PAIR_M
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": CLIPS, "clip_seconds": CLIP_SECONDS,
-                   "frames_per_clip": 199, "weights": source, "accumulate": "fp32",
-                   "l2": "per-step working set ~6 GB of activations >> 126 MB L2 (no explicit flush needed)",
-                   "parallelism": f"dp{world} (utterance-sharded, no data-path collective)"},
+        "config": shared_config(source), "accumulate": "fp32",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(CLIPS * N * 4),
-                "d2h_bytes_per_step": int(CLIPS * 256 * 4), "api": "nomad_b200_embed_host (pinned host buffers)"},
+                "d2h_bytes_per_step": int(CLIPS * 256 * 4 + CLIPS * NMR_M * 4 + CLIPS * 8),
+                "api": "nomad_b200_score_host (pinned host waveforms in; embeddings, distance rows, means out to host)"},
         "gpu_launches": int(launches),
         "step_tflops": step_flops * world / (ms_per_step / 1e3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_pair_kernel (tcgen05 cta_group::2, all 55 GEMM launches of the step)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": GEMM_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_pair_kernel (tcgen05 cta_group::2, all GEMM launches of the step)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "traffic": GEMM_DRAM_TRAFFIC_BYTES, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                      "launches_timed": int(g_n.value), "kernel_ms_per_step": g_ms.value / args.steps,
-                     "kernel_share_of_step": g_ms.value / prof_ms,
-                     "profiled_ms_per_step": prof_ms / args.steps},
-        "pairwise": {"metric": "pairwise distances per second", "n": PAIR_N, "m": PAIR_M, "n_gpus": world,
-                     "value": PAIR_N * PAIR_M * world / (pair_ms / 1e3), "unit": "pairs/s",
-                     "write_GBps_per_gpu": PAIR_N * PAIR_M * 4 / (pair_ms / 1e3) / 1e9,
-                     "means_only_value": PAIR_N * PAIR_M * world / (pair_mean_ms / 1e3),
-                     "roof": "3-pass split-fp16 Gram: 1536 FLOP/pair on the tensor roof, 4 B/pair written on the HBM roof"},
+                     "kernel_share_of_step": g_ms.value / prof_ms, "profiled_ms_per_step": prof_ms / args.steps},
+        "exchange": {"nmr_allgather_ms": allgather_ms, "nmr_allgather_bytes": int(C3_NMR * 256 * 4),
+                     "rows_to_root_ms_per_step": exchange_ms, "rows_to_root_bytes_per_rank": int(CLIPS * NMR_M * 4 + CLIPS * 8),
+                     "collective": "NCCL all_gather_into_tensor + batched isend/irecv to rank 0" if world > 1 else "none (1 rank)"},
+        "sharded_c3": {"workload": f"configs[2] slice, FIXED global: {C3_DEG} degraded + {C3_NMR} NMR utterances, 1-20 s "
+                                   f"(seed 0), masked varlen, through nomad_b200.dist.score_sharded", "scaling": "strong",
+                       "n_gpus": world, "ms": c3_ms, "utt_s": c3_utt_s, "value": c3_utt_s / (c3_ms / 1e3), "unit": UNIT,
+                       "tflops_algorithmic": c3_flops / (c3_ms / 1e3) / 1e12, "pairs": C3_DEG * C3_NMR,
+                       "mean_of_means": c3_check,
+                       "timed": "LPT shard -> embed NMR shard -> all-gather -> embed degraded shard -> cdist rows + means -> "
+                                "means + matrix rows to rank 0 -> D2H of the means; max over ranks"},
+        "pairwise": {"metric": "pairwise distances per second", "workload": f"configs[4] slice, FIXED global {PAIR_N} x {PAIR_M}",
+                     "scaling": "strong", "n": PAIR_N, "m": PAIR_M, "n_gpus": world,
+                     "value": pair_total / (pair_ms / 1e3), "unit": "pairs/s", "ms": pair_ms,
+                     "write_GBps_per_gpu": pair_total / world * 4 / (pair_ms / 1e3) / 1e9,
+                     "hbm_frac_per_gpu": pair_total / world * 4 / (pair_ms / 1e3) / 1e9 / hbm,
+                     "means_only_value": pair_total / (pair_mean_ms / 1e3), "means_only_ms": pair_mean_ms,
+                     "means_only_tensor_frac": 1536.0 * pair_total / world / (pair_mean_ms / 1e3) / 1e12 / peak,
+                     "roof": "3-pass split-fp16 Gram: 1536 FLOP/pair on the tensor roof, 4 B/pair written on the HBM roof; "
+                             "rows sharded across ranks, matrix rows stay with the rank, means to rank 0"},
+        "loss": loss,
         "cpu_baseline": cpu,
+        "parity": parity,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -297,10 +551,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "library"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "library":
+        return run_library(args)
     return run_ours(args)
 
 

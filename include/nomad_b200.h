@@ -99,13 +99,28 @@ NOMAD_B200_API int nomad_b200_layers_fwd(nomad_b200_handle* h, const float* wav_
 
 /* ---- distance: ``cdist(test, nmr)`` + ``np.mean(axis=1)`` (nomad.py:108,111) ---------------------
  * deg: n x 256, nmr: m x 256 fp32 device.  dm (n x m fp32 device, may be NULL when only the means are
- * wanted) and row_mean (n fp64 device).  No handle: the kernel has no weights. */
+ * wanted) and row_mean (n fp64 device; NaN when m == 0, like np.mean of an empty row).  Row means are summed in a
+ * fixed order: bit-identical from run to run.  No handle: the kernel has no weights. */
 NOMAD_B200_API size_t nomad_b200_cdist_workspace_bytes(int64_t n, int64_t m);
 NOMAD_B200_API int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev, int64_t m, float* dm_dev,
                           double* row_mean_dev, void* workspace_dev, size_t workspace_bytes, int gemm_impl,
                           void* stream);
 NOMAD_B200_API int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nmr_host, int64_t m, float* dm_host,
                                double* row_mean_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- one batch of ``Nomad.predict``: the per-file ``model(wave)`` calls (nomad.py:166-189) for B utterances followed by
+ * ``cdist`` + ``np.mean`` of their embeddings against a resident NMR set (nomad.py:108,111) -- one call, no host round
+ * trip in between.  nmr: m x 256 fp32 DEVICE rows (e.g. the all-gathered NMR embeddings of the sharded scoring path).
+ * Outputs: emb B x 256, dm B x m fp32 (may be NULL), row_mean B fp64.  The ``_host`` variant takes the waveforms from
+ * HOST memory (staged H2D overlapping the front end), writes its outputs to HOST memory (emb_host / dm_host may be
+ * NULL) and synchronises the stream. */
+NOMAD_B200_API size_t nomad_b200_score_workspace_bytes(const int64_t* sample_offsets, int B, int64_t m);
+NOMAD_B200_API int nomad_b200_score(nomad_b200_handle* h, const float* wav_dev, const int64_t* sample_offsets, int B,
+                     const float* nmr_dev, int64_t m, float* emb_dev, float* dm_dev, double* row_mean_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+NOMAD_B200_API int nomad_b200_score_host(nomad_b200_handle* h, const float* wav_host, const int64_t* sample_offsets, int B,
+                          const float* nmr_dev, int64_t m, float* emb_host, float* dm_host, double* row_mean_host,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- result formatting: ``df.round(3)`` + ``to_csv`` (nomad.py:113-120, 138-139) without pandas ------------------
  * Writes ``index_name,col_labels...`` then one line per row: ``row_label,v,v,...`` with every value rounded like

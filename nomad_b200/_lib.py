@@ -40,6 +40,11 @@ PROTOTYPES = {
     "nomad_b200_cdist_workspace_bytes": (C.c_size_t, [c_i64, c_i64]),
     "nomad_b200_cdist_mean": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, C.c_int, c_vp]),
     "nomad_b200_cdist_mean_host": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
+    "nomad_b200_score_workspace_bytes": (C.c_size_t, [C.POINTER(c_i64), C.c_int, c_i64]),
+    "nomad_b200_score": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, C.c_size_t,
+                                   c_vp]),
+    "nomad_b200_score_host": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                        C.c_size_t, c_vp]),
     "nomad_b200_gemm_f16": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
     "nomad_b200_write_scores_csv": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), c_i64, C.POINTER(C.c_char_p),

@@ -384,7 +384,6 @@ static int build_weights(Handle* h, TensorTable& tt) {
 static constexpr int META_SLOTS = 4;
 
 int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st) {
-    static thread_local int slot = 0;
     const size_t meta_bytes = sizeof(UttMeta) * p.B, item_bytes = sizeof(uint32_t) * p.attn_items.size();
     const size_t need = align_up(meta_bytes, 64) + item_bytes;
     if (h->meta_cap < need) {
@@ -402,7 +401,8 @@ int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st) 
         h->meta_event = (cudaEvent_t)(void*)ev;
     }
     cudaEvent_t* ev = (cudaEvent_t*)(void*)h->meta_event;
-    slot = (slot + 1) % META_SLOTS;
+    h->meta_slot = (h->meta_slot + 1) % META_SLOTS;  // per handle (a handle is not thread-safe, see the header)
+    const int slot = h->meta_slot;
     NB_CUDA(cudaEventSynchronize(ev[slot]));  // no-op unless this slot's previous copy is still in flight
     char* stage = h->meta_host + (size_t)slot * h->meta_cap;
     memcpy(stage, p.utt.data(), meta_bytes);
@@ -679,6 +679,8 @@ int nomad_b200_set_loss_head(nomad_b200_handle* hh, const float* w, const float*
         NB_TRY(upload_f32(h, w, 256 * 768, &h->w.loss_head_w));
         NB_TRY(upload_f32(h, b, 256, &h->w.loss_head_b));
     } else {
+        // earlier loss steps on the caller's (possibly non-blocking) streams may still read the old head
+        NB_CUDA(cudaDeviceSynchronize());
         NB_CUDA(cudaMemcpy(h->w.loss_head_wt, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
         NB_CUDA(cudaMemcpy(h->w.loss_head_w, w, 256 * 768 * 4, cudaMemcpyHostToDevice));
         NB_CUDA(cudaMemcpy(h->w.loss_head_b, b, 256 * 4, cudaMemcpyHostToDevice));
@@ -720,35 +722,15 @@ static int embed_impl(nomad_b200_handle* hh, const float* wav_dev, const int64_t
     return 0;
 }
 
-extern "C" {
-
-int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
-                     void* workspace_dev, size_t workspace_bytes, void* stream) {
-    return embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, workspace_bytes, stream, nullptr,
-                      [] { return 0; });
-}
-
-int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const int64_t* sample_offsets, int B,
-                          float* emb_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    NB_TRY(check_handle(hh));
-    NB_CHECK(wav_host && emb_host && sample_offsets && B > 0, "embed_host: bad arguments");
+// HOST waveform -> device staging area -> embeddings (device).  H2D in up to 8 utterance groups on a side stream; the
+// compute stream picks each group up as it lands (front end of group g overlaps the copy of group g + 1).  The first
+// group is half the size of the others so that the GPU starts computing as early as possible.
+static int embed_staged(nomad_b200_handle* hh, const float* wav_host, float* wav_dev, const int64_t* sample_offsets, int B,
+                        float* emb_dev, void* workspace_dev, size_t core_bytes, void* stream) {
     Handle* h = &hh->h;
     NB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = sample_offsets[B] - sample_offsets[0];
-    // the tail of the caller's workspace holds the staged waveform and the embeddings
-    Plan p;
-    NB_TRY(make_plan(sample_offsets, B, &p));
-    const size_t core = carve_workspace(p, nullptr, nullptr, false);
-    const size_t wav_bytes = align_up((size_t)total * 4 + 64, 1024), emb_bytes = align_up((size_t)B * EMB * 4, 1024);
-    NB_CHECK(workspace_bytes >= core + wav_bytes + emb_bytes,
-             "embed_host: workspace too small (%zu < %zu bytes; embed_workspace_bytes + 4*samples + 1024*B + 4096)",
-             workspace_bytes, core + wav_bytes + emb_bytes);
-    float* wav_dev = (float*)((char*)workspace_dev + core);
-    float* emb_dev = (float*)((char*)workspace_dev + core + wav_bytes);
-    // H2D in up to 8 utterance groups on a side stream; the compute stream picks each group up as it lands (front end
-    // of group g overlaps the copy of group g + 1).  The first group is half the size of the others so that the
-    // GPU starts computing as early as possible.
     static const int max_groups = getenv("NOMAD_B200_H2D_GROUPS") ? atoi(getenv("NOMAD_B200_H2D_GROUPS")) : 8;
     FrontPipe pipe;
     if (!h->copy_stream) {
@@ -782,7 +764,34 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
         }
         return 0;
     };
-    NB_TRY(embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, core, stream, &pipe, issue_copies));
+    return embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, core_bytes, stream, &pipe, issue_copies);
+}
+
+extern "C" {
+
+int nomad_b200_embed(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B, float* emb_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return embed_impl(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, workspace_bytes, stream, nullptr,
+                      [] { return 0; });
+}
+
+int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const int64_t* sample_offsets, int B,
+                          float* emb_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_TRY(check_handle(hh));
+    NB_CHECK(wav_host && emb_host && sample_offsets && B > 0, "embed_host: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = sample_offsets[B] - sample_offsets[0];
+    // the tail of the caller's workspace holds the staged waveform and the embeddings
+    Plan p;
+    NB_TRY(make_plan(sample_offsets, B, &p));
+    const size_t core = carve_workspace(p, nullptr, nullptr, false);
+    const size_t wav_bytes = align_up((size_t)total * 4 + 64, 1024), emb_bytes = align_up((size_t)B * EMB * 4, 1024);
+    NB_CHECK(workspace_bytes >= core + wav_bytes + emb_bytes,
+             "embed_host: workspace too small (%zu < %zu bytes; embed_workspace_bytes + 4*samples + 1024*B + 4096)",
+             workspace_bytes, core + wav_bytes + emb_bytes);
+    float* wav_dev = (float*)((char*)workspace_dev + core);
+    float* emb_dev = (float*)((char*)workspace_dev + core + wav_bytes);
+    NB_TRY(embed_staged(hh, wav_host, wav_dev, sample_offsets, B, emb_dev, workspace_dev, core, stream));
     NB_CUDA(cudaMemcpyAsync(emb_host, emb_dev, (size_t)B * EMB * 4, cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -873,7 +882,8 @@ static bool cdist_use_tc(int64_t n, int64_t m, int gemm_impl) { return gemm_impl
 
 size_t nomad_b200_cdist_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
-    return cdist_use_tc(n, m, 0) ? cdist_tc_workspace(n, m) : 1024;
+    const size_t a = cdist_use_tc(n, m, 0) ? cdist_tc_workspace(n, m) : 0, b = cdist_fp32_workspace(n, m);
+    return a > b ? a : b;  // the SIMT cross-check of a large problem takes the fp32 kernel
 }
 
 int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev, int64_t m, float* dm_dev,
@@ -885,7 +895,57 @@ int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev,
     if (cdist_use_tc(n, m, gemm_impl))
         return launch_cdist_tc((cudaStream_t)stream, deg_dev, n, nmr_dev, m, dm_dev, row_mean_dev, workspace_dev,
                                workspace_bytes, 0);
-    return launch_cdist_fp32((cudaStream_t)stream, deg_dev, n, nmr_dev, m, dm_dev, row_mean_dev);
+    return launch_cdist_fp32((cudaStream_t)stream, deg_dev, n, nmr_dev, m, dm_dev, row_mean_dev, workspace_dev,
+                             workspace_bytes);
+}
+
+// ---- one batch of Nomad.predict: embed + distance rows against a resident NMR set ---------------------------------
+size_t nomad_b200_score_workspace_bytes(const int64_t* sample_offsets, int B, int64_t m) {
+    const size_t e = nomad_b200_embed_workspace_bytes(sample_offsets, B);
+    if (e == 0 || m < 0) return 0;
+    const long long total = sample_offsets[B] - sample_offsets[0];
+    // embed workspace | cdist workspace | staged waveform, embeddings, matrix rows, means (the *_host variant)
+    return align_up(e, 1024) + align_up(nomad_b200_cdist_workspace_bytes(B, m), 1024) + align_up((size_t)total * 4 + 64, 1024) +
+           align_up((size_t)B * EMB * 4, 1024) + align_up((size_t)B * (size_t)m * 4, 1024) + align_up((size_t)B * 8, 1024);
+}
+
+int nomad_b200_score(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B,
+                     const float* nmr_dev, int64_t m, float* emb_dev, float* dm_dev, double* row_mean_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_CHECK(sample_offsets && B > 0 && m >= 0 && emb_dev && row_mean_dev, "score: bad arguments");
+    const size_t e = align_up(nomad_b200_embed_workspace_bytes(sample_offsets, B), 1024);
+    NB_CHECK(e != 0, "score: %s", nomad_b200_last_error());
+    const size_t c = nomad_b200_cdist_workspace_bytes(B, m);
+    NB_CHECK(workspace_dev && workspace_bytes >= e + c, "score: workspace too small (%zu < %zu bytes)", workspace_bytes, e + c);
+    NB_TRY(nomad_b200_embed(hh, wav_dev, sample_offsets, B, emb_dev, workspace_dev, e, stream));
+    return nomad_b200_cdist_mean(emb_dev, B, nmr_dev, m, dm_dev, row_mean_dev, (char*)workspace_dev + e, c, 0, stream);
+}
+
+int nomad_b200_score_host(nomad_b200_handle* hh, const float* wav_host, const int64_t* sample_offsets, int B,
+                          const float* nmr_dev, int64_t m, float* emb_host, float* dm_host, double* row_mean_host,
+                          void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_TRY(check_handle(hh));
+    NB_CHECK(wav_host && sample_offsets && B > 0 && m >= 0 && row_mean_host, "score_host: bad arguments");
+    const size_t need = nomad_b200_score_workspace_bytes(sample_offsets, B, m);
+    NB_CHECK(need != 0, "score_host: %s", nomad_b200_last_error());
+    NB_CHECK(workspace_dev && workspace_bytes >= need, "score_host: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    const long long total = sample_offsets[B] - sample_offsets[0];
+    const size_t e = align_up(nomad_b200_embed_workspace_bytes(sample_offsets, B), 1024);
+    const size_t c = align_up(nomad_b200_cdist_workspace_bytes(B, m), 1024);
+    char* base = (char*)workspace_dev;
+    float* wav_dev = (float*)(base + e + c);
+    float* emb_dev = (float*)((char*)wav_dev + align_up((size_t)total * 4 + 64, 1024));
+    float* dm_dev = (float*)((char*)emb_dev + align_up((size_t)B * EMB * 4, 1024));
+    double* rm_dev = (double*)((char*)dm_dev + align_up((size_t)B * (size_t)m * 4, 1024));
+    cudaStream_t st = (cudaStream_t)stream;
+    // waveform H2D in utterance groups on the side stream, front end of group g overlapping the copy of group g + 1
+    NB_TRY(embed_staged(hh, wav_host, wav_dev, sample_offsets, B, emb_dev, workspace_dev, e, stream));
+    NB_TRY(nomad_b200_cdist_mean(emb_dev, B, nmr_dev, m, dm_host ? dm_dev : nullptr, rm_dev, base + e, c, 0, stream));
+    if (emb_host) NB_CUDA(cudaMemcpyAsync(emb_host, emb_dev, (size_t)B * EMB * 4, cudaMemcpyDeviceToHost, st));
+    if (dm_host && m > 0) NB_CUDA(cudaMemcpyAsync(dm_host, dm_dev, (size_t)B * (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(row_mean_host, rm_dev, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, const float* nmr_host, int64_t m, float* dm_host,

@@ -381,10 +381,10 @@ int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items,
             fn = reinterpret_cast<EncodeTiledFnFa>(p);
     });
     NB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    if (bool* flag = device_once_flag(attr_set)) {
         NB_CUDA(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        attr_set = true;
+        *flag = true;
     }
     if (n_items <= 0) return 0;
     CUtensorMap tmq, tmkv;

@@ -50,6 +50,14 @@ void count_launch();
         NB_CUDA(cudaGetLastError());  \
     } while (0)
 
+// "done once per device" state for per-device settings (cudaFuncSetAttribute is per device/context): returns the flag
+// of the CURRENT device if it is still unset, nullptr otherwise.
+inline bool* device_once_flag(bool (&flags)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return flags[dev] ? nullptr : &flags[dev];
+}
+
 #define NB_TRY(expr)            \
     do {                        \
         int _r = (expr);        \

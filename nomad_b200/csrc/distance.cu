@@ -15,7 +15,7 @@ static constexpr int CD_TILE = 64, CD_K = 32, CD_DIM = 256;
 
 __global__ void __launch_bounds__(256) cdist_fp32_kernel(const float* __restrict__ a, long long n,
                                                          const float* __restrict__ b, long long m,
-                                                         float* __restrict__ dm, double* __restrict__ row_sum) {
+                                                         float* __restrict__ dm, double* __restrict__ row_part) {
     __shared__ __align__(16) float As[CD_K][CD_TILE + 4];
     __shared__ __align__(16) float Bs[CD_K][CD_TILE + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) cdist_fp32_kernel(const float* __restrict
                     if (col < m) dm[row * m + col] = d[j];
                 }
             }
-            if (tx == 0) atomicAdd(row_sum + row, s);
+            if (tx == 0) row_part[(long long)blockIdx.x * n + row] = s;  // one writer per (column tile, row)
         }
     }
 }
@@ -115,6 +115,18 @@ int launch_paired_dist(cudaStream_t st, const float* a, const float* b, long lon
 __global__ void scale_rows_kernel(double* v, long long n, double s) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] *= s;
+}
+
+// Row means from the per-(column group, row) partial sums, added in a fixed order (np.mean(axis=1), nomad.py:111):
+// bit-identical from run to run, unlike atomics whose order depends on tile scheduling.
+template <typename T>
+__global__ void __launch_bounds__(256) row_mean_finish_kernel(const T* __restrict__ part, long long n, int groups,
+                                                              double inv_m, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int g = 0; g < groups; ++g) s += (double)part[(long long)g * n + i];
+    out[i] = s * inv_m;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -156,14 +168,20 @@ __global__ void __launch_bounds__(256) cdist_prep_kernel(const float* __restrict
 
 size_t cdist_tc_workspace(long long n, long long m) {
     auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
-    return al((size_t)n * 3 * CD_DIM * 2) + al((size_t)m * 3 * CD_DIM * 2) + al((size_t)n * 4) + al((size_t)m * 4) + 1024;
+    return al((size_t)n * 3 * CD_DIM * 2) + al((size_t)m * 3 * CD_DIM * 2) + al((size_t)n * 4) + al((size_t)m * 4) +
+           al((size_t)n * 4 * (size_t)cdist_row_groups(n, m)) + 1024;
+}
+size_t cdist_fp32_workspace(long long n, long long m) {
+    return (size_t)n * 8 * (size_t)((m + CD_TILE - 1) / CD_TILE) + 1024;
 }
 
 int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
                     double* row_mean, void* ws, size_t ws_bytes, int impl) {
     if (n <= 0) return 0;
-    NB_CUDA(cudaMemsetAsync(row_mean, 0, sizeof(double) * n, st));
-    if (m <= 0) return 0;
+    if (m <= 0) {  // np.mean of an empty row is NaN (the reference would print NaN scores)
+        NB_CUDA(cudaMemsetAsync(row_mean, 0xFF, sizeof(double) * n, st));
+        return 0;
+    }
     NB_CHECK(ws != nullptr && ws_bytes >= cdist_tc_workspace(n, m), "cdist: workspace too small (%zu < %zu bytes)", ws_bytes,
              cdist_tc_workspace(n, m));
     NB_CHECK(n < (1LL << 31) && m < (1LL << 31), "cdist: too many rows for one call; chunk it");
@@ -173,6 +191,9 @@ int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b
     op_t* sb = (op_t*)(base + al((size_t)n * 3 * CD_DIM * 2));
     float* na = (float*)((char*)sb + al((size_t)m * 3 * CD_DIM * 2));
     float* nbv = (float*)((char*)na + al((size_t)n * 4));
+    float* part = (float*)((char*)nbv + al((size_t)m * 4));
+    const int groups = cdist_row_groups(n, m);
+    if (impl != 0) NB_CUDA(cudaMemsetAsync(row_mean, 0, sizeof(double) * n, st));  // SIMT check kernel: atomics
     cdist_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, n, 0, sa, na);
     NB_LAUNCHED();
     cdist_prep_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(b, m, 1, sb, nbv);
@@ -187,25 +208,34 @@ int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b
     e.norm_a = na;
     e.norm_b = nbv;
     e.row_sum = row_mean;
+    e.row_part = part;
     e.cd_a = a;
     e.cd_b = b;
     e.cd_inv_scale = 1.0f / (CD_SCALE * CD_SCALE);
     NB_TRY(gemm_h16(st, A, Bw, (int)n, (int)m, 3 * CD_DIM, 1, e, impl));
-    scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_mean, n, 1.0 / (double)m);
+    if (impl != 0)
+        scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_mean, n, 1.0 / (double)m);
+    else
+        row_mean_finish_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n, groups, 1.0 / (double)m, row_mean);
     NB_LAUNCHED();
     return 0;
 }
 
 int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
-                      double* row_mean) {
+                      double* row_mean, void* ws, size_t ws_bytes) {
     if (n <= 0) return 0;
-    NB_CUDA(cudaMemsetAsync(row_mean, 0, sizeof(double) * n, st));
-    if (m <= 0) return 0;
+    if (m <= 0) {  // np.mean of an empty row is NaN
+        NB_CUDA(cudaMemsetAsync(row_mean, 0xFF, sizeof(double) * n, st));
+        return 0;
+    }
+    NB_CHECK(ws != nullptr && ws_bytes >= cdist_fp32_workspace(n, m), "cdist: workspace too small (%zu < %zu bytes)", ws_bytes,
+             cdist_fp32_workspace(n, m));
     dim3 grid((unsigned)((m + CD_TILE - 1) / CD_TILE), (unsigned)((n + CD_TILE - 1) / CD_TILE));
     NB_CHECK(grid.y <= 65535u, "cdist: too many rows for one launch (%lld); chunk the call", n);
-    cdist_fp32_kernel<<<grid, 256, 0, st>>>(a, n, b, m, dm, row_mean);
+    double* part = (double*)ws;
+    cdist_fp32_kernel<<<grid, 256, 0, st>>>(a, n, b, m, dm, part);
     NB_LAUNCHED();
-    scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_mean, n, 1.0 / (double)m);
+    row_mean_finish_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n, (int)grid.x, 1.0 / (double)m, row_mean);
     NB_LAUNCHED();
     return 0;
 }

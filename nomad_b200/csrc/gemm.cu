@@ -376,7 +376,7 @@ template <int CHUNKS, bool PAIR, bool CDIST, int EF>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
-                                              const float* vec = nullptr, int vec_stride = 0) {
+                                              const float* vec = nullptr, int vec_stride = 0, int cd_group = 0) {
     const bool row_ok = row < args.M;
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
@@ -425,7 +425,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
         }
     }
     rhave = rc.rhave;
-    if (CDIST && row_ok) atomicAdd(args.epi.row_sum + row, row_sum);
+    // one writer per (column group, row): the row means come out bit-identical from run to run (no atomics)
+    if (CDIST && row_ok) args.epi.row_part[(long long)cd_group * args.M + row] = (float)row_sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -550,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             epilogue_tile<CHUNKS, false, CDIST, -1>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                         row_st, nullptr, no_prefetch, nullptr);
+                                         row_st, nullptr, no_prefetch, nullptr, nullptr, 0, n_blk * 2 + h);
         }
     }
     tc_fence_before();
@@ -747,7 +748,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             epilogue_tile<HALF / 32, true, CDIST, EF>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                           row_st, rbuf, rhave, next_src, vec, HALF);
+                                           row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h);
         }
     }
     tc_fence_before();
@@ -843,6 +844,18 @@ int device_sm_count() {
     return sms[dev];
 }
 
+static bool use_pair_kernel(int M, int N, int batch) {
+    static const int use_pair = getenv("NOMAD_B200_PAIR") ? atoi(getenv("NOMAD_B200_PAIR")) : 1;
+    return use_pair && N >= 256 && (long long)((M + 255) / 256) * ((N + 255) / 256) * batch >= device_sm_count() / 2;
+}
+// must mirror the kernel choice of gemm_h16 for EPI_CDIST: pair kernel = 16 epilogue warps (4 column groups per
+// 256-wide tile); single-CTA kernels = 2 column groups per BN-wide tile (BN = 256 / 128 / 64; EPI_CDIST never takes 192)
+int cdist_row_groups(long long n, long long m) {
+    if (use_pair_kernel((int)n, (int)m, 1)) return (int)((m + 255) / 256) * 4;
+    const int bn = m > 128 ? 256 : (m > 64 ? 128 : 64);
+    return (int)((m + bn - 1) / bn) * 2;
+}
+
 // In-situ timing of the tensor-core GEMM launches (bench.py's roofline leg): one CUDA event pair per
 // launch on the launching stream, read back after the timed region.
 struct GemmProfile {
@@ -897,10 +910,10 @@ static int prof_end(cudaStream_t st) {
 template <int BN, bool CDIST>
 static int launch_tc_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = TileCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    if (bool* flag = device_once_flag(attr_set)) {
         NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        *flag = true;
     }
     CUtensorMap tmA, tmB;
     NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
@@ -925,10 +938,10 @@ template <int NEW, bool CDIST, bool RPF = false, int EF = -1>
 static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
     constexpr int SMEM = Cfg::smem_bytes(NEW, RPF);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    if (bool* flag = device_once_flag(attr_set)) {
         NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
+        *flag = true;
     }
     CUtensorMap tmA, tmB;
     NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
@@ -1020,9 +1033,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         return 0;
     }
     // CTA pairs (cta_group::2) for the big GEMMs; NOMAD_B200_PAIR=0 falls back to the single-CTA kernel
-    static const int use_pair = getenv("NOMAD_B200_PAIR") ? atoi(getenv("NOMAD_B200_PAIR")) : 1;
-    if (use_pair && N >= 256 && (long long)((M + 255) / 256) * ((N + 255) / 256) * batch >= device_sm_count() / 2)
-        return launch_pair(st, A, B, args);
+    if (use_pair_kernel(M, N, batch)) return launch_pair(st, A, B, args);
     if (N > 128) {
         // 256-wide tiles unless 192-wide ones waste enough fewer CTA-waves to pay for their lower per-tile
         // efficiency (measured 0.89 on B200, profiles/r01_gemm_probe_v2.log)
@@ -1033,7 +1044,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
             const double used = (double)N / (((N + bn - 1) / bn) * (double)bn);
             return tile_eff * used * tiles / (std::ceil(tiles / sms) * sms);
         };
-        const bool use192 = (epi.flags & EPI_STATS_OUT) ? false : (force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0));
+        const bool use192 = (epi.flags & (EPI_STATS_OUT | EPI_CDIST)) ? false : (force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0));
         if (use192) {
             args.umma_n = 192;
             return launch_tc<192>(st, A, B, args);

@@ -13,7 +13,7 @@ enum : int {
     EPI_OUT_F32 = 8,   // store fp32
     EPI_OUT_H16 = 16, // store op_t
     EPI_MUL_AUX = 32,  // * aux[row, col] (op_t)  -- dgrad through GELU: aux holds gelu'(pre-activation)
-    EPI_CDIST = 64,
+    EPI_CDIST = 64,    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + per-column-group partial row sums
     EPI_RESID_LN = 256,  // + LayerNorm(resid row) recomputed from saved (mean, rstd): (r - mean) * rstd * g + b
     // LayerNorm of the A operand folded into this GEMM: A holds the UN-normalised rows x, the weights carry gamma
     // (W' = W diag(gamma)), and out = rstd_r * (acc - mean_r * s[col]) + c[col] with s = row sums of W' and
@@ -22,7 +22,7 @@ enum : int {
     // also emit per-row partial LayerNorm statistics of the fp32 output, one (mean, M2) pair per 64 columns, for
     // a later EPI_LN_FOLD / EPI_RESID_LN consumer (needs N % 256 == 0)
     EPI_STATS_OUT = 1024,
-    EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward    // out = sqrt(max(na[row] + nb[col] - 2 acc, 0)); fp32 store + fp64 row-sum atomics
+    EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward
 };
 
 // One operand: ``rows`` rows of K op_t values, row r of batch b starting at
@@ -63,7 +63,9 @@ struct GemmEpilogue {
     // EPI_CDIST: acc = cd_scale^-1 * <a_row, b_col> from split-fp16 operands
     const float* norm_a;      // [M] squared norms of the rows of A
     const float* norm_b;      // [N]
-    double* row_sum;          // [M] += sum over cols of the distances
+    double* row_sum;          // SIMT check kernel only: [M] += sum over cols of the distances (atomics)
+    float* row_part;          // tensor-core kernels: [column groups][M] partial row sums, each written exactly once
+                              // (group = 64- or 128-column slice owned by one epilogue warp) -> deterministic means
     const float* cd_a;        // [M][256] original fp32 rows (exact re-evaluation of near-zero distances)
     const float* cd_b;        // [N][256]
     float cd_inv_scale;       // acc * cd_inv_scale = dot product
@@ -76,6 +78,8 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
               const GemmEpilogue& epi, int impl);
 
 int device_sm_count();
+// column groups (partial row sums per row) the EPI_CDIST tensor-core kernels write for an n x m problem
+int cdist_row_groups(long long n, long long m);
 
 // event-pair timing of every tensor-core GEMM launch while enabled (see bench.py)
 void gemm_profile_enable(bool on);

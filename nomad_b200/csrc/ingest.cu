@@ -165,7 +165,10 @@ int nomad_b200_ingest_pcm16(const int16_t* pcm_dev, int64_t n_frames, int channe
     const int win_cap = (256 / t.n + 2) * t.o + t.K;
     const size_t smem = (size_t)win_cap * sizeof(float);
     NB_CHECK(smem <= 200 * 1024, "ingest: resampling %d -> %d Hz needs %zu bytes of shared memory per block", sr, target_sr, smem);
-    static size_t smem_set = 0;
+    static size_t smem_set_dev[64] = {0};  // the attribute is per device
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    size_t& smem_set = smem_set_dev[cur_dev];
     if (smem > 48 * 1024 && smem > smem_set) {
         NB_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;

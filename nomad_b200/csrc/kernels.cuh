@@ -42,8 +42,9 @@ int launch_posconv(cudaStream_t st, const op_t* pos_g, long long rows_alloc, lon
                    const float* bias, int flags, op_t* out, op_t* aux_out);
 
 // ---- distance.cu
+size_t cdist_fp32_workspace(long long n, long long m);
 int launch_cdist_fp32(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,
-                      double* row_mean);
+                      double* row_mean, void* ws, size_t ws_bytes);
 int launch_paired_dist(cudaStream_t st, const float* a, const float* b, long long n, double* out);
 size_t cdist_tc_workspace(long long n, long long m);
 int launch_cdist_tc(cudaStream_t st, const float* a, long long n, const float* b, long long m, float* dm,

@@ -131,6 +131,7 @@ struct Handle {
     bool has_loss_head = false;
     char* meta_host = nullptr;  // pinned staging for the per-call metadata (UttMeta[B] + attention work list)
     size_t meta_cap = 0;        // bytes per staging slot
+    int meta_slot = 0;          // staging slot of the most recent call
     cudaEvent_t meta_event = nullptr;  // last use of meta_host by an async copy
     cudaStream_t copy_stream = nullptr;  // H2D side stream of the *_host entry points
     cudaEvent_t fork_event = nullptr;

@@ -265,10 +265,10 @@ int launch_posconv(cudaStream_t st, const op_t* pos_g, long long rows_alloc, lon
                    const float* bias, int flags, op_t* out, op_t* aux_out) {
     EncodeTiledFn2 fn = encode_fn();
     NB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    if (bool* flag = device_once_flag(attr_set)) {
         NB_CUDA(cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
-        attr_set = true;
+        *flag = true;
     }
     CUtensorMap tmSlab, tmW;
     {

@@ -1,14 +1,22 @@
 """Multi-GPU scoring: one process per GPU, utterances sharded across ranks, ONE collective exchange.
 
 The reference has no distributed code; this is the natural sharding of its scoring
-path: utterances are independent, so NMR and degraded files are partitioned across
-ranks by audio length (LPT greedy), each rank embeds its NMR shard, the (M, 256) NMR embeddings are
-all-gathered once (NCCL over NVLink on GPUs; <= 8 MB, latency bound), each rank then embeds its
-degraded shard and computes its rows of the distance matrix and their means locally.  Row results are
-gathered on rank 0 and restored to listing order, so outputs are identical to the single-GPU run.
+path (``nomad.py:102-111``).  Utterances are independent, so NMR and degraded files are
+partitioned across ranks by audio length (LPT greedy; every rank computes the same partition, so no
+sizes are exchanged):
 
-The functions take ``embed_fn`` / ``cdist_fn`` callables so the host logic is exercised by
-world_size-2 ``gloo`` tests on CPU.
+1. each rank embeds its NMR shard;
+2. ONE all-gather of the (M, 256) fp32 NMR embeddings (NCCL over NVLink/NVSwitch; <= 8 MB, latency
+   bound), issued asynchronously so that it overlaps the start of step 3;
+3. each rank embeds its degraded shard and computes its rows of the distance matrix and their means
+   against the full NMR set;
+4. row means -- and, when wanted, the matrix rows -- are sent to rank 0 only (point-to-point inside the
+   group communicator, exact sizes, no padding), where listing order is restored.  The distance matrix
+   is never all-gathered; for corpora whose matrix should not live on one rank ``matrix='local'``
+   leaves each rank's rows with the rank (row-sharded files).
+
+The functions take ``embed`` / ``cdist_fn`` callables so the host logic is exercised by world_size-2
+``gloo`` tests on CPU, and so that ``bench.py`` times exactly the code ``predict_sharded`` runs.
 """
 from __future__ import annotations
 
@@ -37,71 +45,128 @@ def _world(group=None):
     return 0, 1
 
 
-def all_gather_rows(local: torch.Tensor, group=None) -> List[torch.Tensor]:
-    """All-gather row blocks of different heights: pad to the tallest, one all_gather, un-pad."""
+def _listing_index(shards: List[List[int]], stride: int, device) -> torch.Tensor:
+    """Row of listing position i inside a buffer that stores shard r at rows [r * stride, r * stride + len)."""
+    n = sum(len(s) for s in shards)
+    src = np.empty((n,), dtype=np.int64)
+    for r, s in enumerate(shards):
+        if s:
+            src[np.asarray(s, dtype=np.int64)] = r * stride + np.arange(len(s), dtype=np.int64)
+    return torch.from_numpy(src).to(device)
+
+
+class _Pending:
+    """An all-gather in flight; ``result()`` waits (stream-ordered on CUDA) and restores listing order."""
+
+    def __init__(self, work, buf, index):
+        self.work, self.buf, self.index = work, buf, index
+
+    def result(self) -> torch.Tensor:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        return self.buf.index_select(0, self.index)
+
+
+def all_gather_shards(local: torch.Tensor, shards: List[List[int]], group=None, async_op: bool = False):
+    """``local`` = this rank's rows (len(shards[rank]), d) in shard order.  ONE all-gather (shards padded to the
+    tallest); returns all rows in listing order on every rank -- or a ``_Pending`` when ``async_op``."""
     rank, world = _world(group)
+    d = local.shape[1]
+    tall = max(1, max(len(s) for s in shards))
+    assert local.shape[0] == len(shards[rank])
+    index = _listing_index(shards, tall, local.device)
     if world == 1:
-        return [local]
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
-    tall = max(max(counts), 1)
-    pad = torch.zeros((tall,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pend = _Pending(None, local, index)
+        return pend if async_op else pend.result()
+    pad = torch.zeros((tall, d), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad, group=group)
-    return [o[:c] for o, c in zip(outs, counts)]
+    buf = torch.empty((world * tall, d), dtype=local.dtype, device=local.device)
+    work = dist.all_gather_into_tensor(buf, pad, group=group, async_op=True)
+    pend = _Pending(work, buf, index)
+    return pend if async_op else pend.result()
 
 
-def sharded_embeddings(costs: Sequence[float], load_and_embed: Callable[[List[int]], torch.Tensor], dim: int,
-                       device, group=None) -> torch.Tensor:
+def gather_shards_to_root(local: torch.Tensor, shards: List[List[int]], group=None) -> Optional[torch.Tensor]:
+    """Send every rank's row block to rank 0 only (exact sizes, one batch of point-to-point operations in the group's
+    communicator).  Rank 0 returns the rows in listing order (same device); other ranks return ``None``."""
+    rank, world = _world(group)
+    assert local.shape[0] == len(shards[rank])
+    if world == 1:
+        return local.index_select(0, _listing_index(shards, 0, local.device)) if local.shape[0] else local
+    local = local.contiguous()
+    if rank != 0:
+        if local.shape[0]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dist.get_global_rank(group, 0) if group else 0,
+                                                        group=group)]):
+                w.wait()
+        return None
+    n = sum(len(s) for s in shards)
+    buf = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    starts = np.concatenate([[0], np.cumsum([len(s) for s in shards])]).astype(np.int64)
+    buf[: local.shape[0]] = local
+    ops = []
+    for r in range(1, world):
+        if shards[r]:
+            peer = dist.get_global_rank(group, r) if group else r
+            ops.append(dist.P2POp(dist.irecv, buf[starts[r]: starts[r + 1]], peer, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    # buf stores shard r at rows [starts[r], starts[r+1]): listing position i -> its row
+    src = np.empty((n,), dtype=np.int64)
+    for r, s in enumerate(shards):
+        if s:
+            src[np.asarray(s, dtype=np.int64)] = starts[r] + np.arange(len(s), dtype=np.int64)
+    return buf.index_select(0, torch.from_numpy(src).to(buf.device))
+
+
+def sharded_embeddings(costs: Sequence[float], embed: Callable[[List[int]], torch.Tensor], dim: int,
+                       device, group=None, async_op: bool = False):
     """Every rank embeds its shard; returns ALL embeddings (len(costs), dim) in listing order on every rank."""
     rank, world = _world(group)
     shards = shard_by_cost(costs, world)
     mine = shards[rank]
-    local = load_and_embed(mine) if mine else torch.zeros((0, dim), dtype=torch.float32, device=device)
-    parts = all_gather_rows(local.to(device=device, dtype=torch.float32).contiguous(), group)
-    full = torch.empty((len(costs), dim), dtype=torch.float32, device=device)
-    for s, p in zip(shards, parts):
-        if s:
-            full[torch.as_tensor(s, dtype=torch.long, device=device)] = p
-    return full
+    local = embed(mine) if mine else torch.zeros((0, dim), dtype=torch.float32, device=device)
+    local = local.to(device=device, dtype=torch.float32).contiguous()
+    return all_gather_shards(local, shards, group, async_op=async_op)
 
 
-def sharded_scores(deg_costs: Sequence[float], load_and_embed: Callable[[List[int]], torch.Tensor],
-                   nmr_emb: torch.Tensor, cdist_fn: Callable, device, group=None, want_matrix: bool = True):
-    """Each rank: embed its degraded shard, distance rows + means vs the full NMR set.  Rank 0 gets
-    ``(dm (N, M) float64 | None, mean (N,) float64, deg_emb (N, dim))`` in listing order; other ranks ``None``."""
+def sharded_scores(deg_costs: Sequence[float], embed: Callable[[List[int]], torch.Tensor], nmr_emb,
+                   cdist_fn: Callable, device, group=None, matrix: str = "root", want_emb: bool = False):
+    """Each rank: embed its degraded shard, distance rows + means against the full NMR set (``nmr_emb``: tensor or
+    the pending all-gather).  ``matrix``: "root" (rows sent to rank 0), "local" (rows stay on the rank that computed
+    them) or "none".  Returns a dict: on rank 0 ``mean`` (N,) float64 and ``dm`` (N, M) float32 (matrix="root") in
+    listing order; on every rank ``local_rows`` (listing indices of its shard), ``local_mean`` and, for
+    matrix="local", ``local_dm``.  Tensors stay on ``device``; nothing is synchronised here."""
+    assert matrix in ("root", "local", "none")
     rank, world = _world(group)
     shards = shard_by_cost(deg_costs, world)
     mine = shards[rank]
-    dim = nmr_emb.shape[1]
+    emb = (embed(mine).to(device=device, dtype=torch.float32) if mine
+           else torch.zeros((0, 256), dtype=torch.float32, device=device))
+    if isinstance(nmr_emb, _Pending):
+        nmr_emb = nmr_emb.result()
     M = nmr_emb.shape[0]
     if mine:
-        emb = load_and_embed(mine).to(device=device, dtype=torch.float32)
-        dm, mean = cdist_fn(emb, nmr_emb, want_matrix)
+        dm, mean = cdist_fn(emb, nmr_emb, matrix != "none")
     else:
-        emb = torch.zeros((0, dim), dtype=torch.float32, device=device)
-        dm = torch.zeros((0, M), dtype=torch.float32, device=device) if want_matrix else None
+        dm = torch.zeros((0, M), dtype=torch.float32, device=device) if matrix != "none" else None
         mean = torch.zeros((0,), dtype=torch.float64, device=device)
-    mean_parts = all_gather_rows(mean.reshape(-1, 1).to(torch.float64).contiguous(), group)
-    emb_parts = all_gather_rows(emb.contiguous(), group)
-    dm_parts = all_gather_rows(dm.to(torch.float32).contiguous(), group) if want_matrix else None
-    if rank != 0:
-        return None
-    N = len(deg_costs)
-    out_mean = np.empty((N,), dtype=np.float64)
-    out_emb = np.empty((N, dim), dtype=np.float32)
-    out_dm = np.empty((N, M), dtype=np.float64) if want_matrix else None
-    for r, s in enumerate(shards):
-        if not s:
-            continue
-        out_mean[s] = mean_parts[r].reshape(-1).cpu().numpy()
-        out_emb[s] = emb_parts[r].cpu().numpy()
-        if want_matrix:
-            out_dm[s] = dm_parts[r].cpu().numpy().astype(np.float64)
-    return out_dm, out_mean, out_emb
+    out = {"local_rows": mine, "local_mean": mean, "local_dm": dm if matrix == "local" else None, "nmr": nmr_emb}
+    got = gather_shards_to_root(mean.reshape(-1, 1).to(torch.float64), shards, group)
+    out["mean"] = got.reshape(-1) if got is not None else None
+    out["dm"] = gather_shards_to_root(dm.to(torch.float32), shards, group) if matrix == "root" else None
+    if want_emb:
+        out["emb"] = gather_shards_to_root(emb, shards, group)
+    return out
+
+
+def score_sharded(nmr_costs: Sequence[float], embed_nmr: Callable, deg_costs: Sequence[float], embed_deg: Callable,
+                  cdist_fn: Callable, device, group=None, matrix: str = "root", want_emb: bool = False):
+    """Steps 1-4 of the module docstring.  The NMR all-gather is in flight while the degraded shard is embedded."""
+    pending = sharded_embeddings(nmr_costs, embed_nmr, 256, device, group, async_op=True)
+    return sharded_scores(deg_costs, embed_deg, pending, cdist_fn, device, group, matrix, want_emb)
 
 
 def init_from_env(backend: Optional[str] = None):
@@ -120,9 +185,16 @@ def init_from_env(backend: Optional[str] = None):
     return rank, world, local
 
 
-def predict_sharded(nomad, mode: str, nmr: str, deg: str, results_path: Optional[str] = None, group=None):
-    """``Nomad.predict`` across the ranks of the current process group.  Rank 0 returns
-    ``(df_avg_nomad, df_dm)`` and writes the CSVs; other ranks return ``None``."""
+# above this many matrix bytes the rows stay with the ranks and are written as row-sharded files
+ROOT_MATRIX_LIMIT_BYTES = 8 << 30
+
+
+def predict_sharded(nomad, mode: str, nmr: str, deg: str, results_path: Optional[str] = None, group=None,
+                    matrix: Optional[str] = None):
+    """``Nomad.predict`` across the ranks of the current process group.  Rank 0 returns ``(df_avg_nomad, df_dm)`` and
+    writes the CSVs; other ranks return ``None``.  With ``matrix='local'`` (default above ROOT_MATRIX_LIMIT_BYTES)
+    every rank writes its own rows to ``nomad_scores.rank<r>.csv`` under ``results_path`` and rank 0 returns
+    ``(df_avg_nomad, None)``."""
     import pandas as pd
 
     rank, world = _world(group)
@@ -140,18 +212,26 @@ def predict_sharded(nomad, mode: str, nmr: str, deg: str, results_path: Optional
         return obj[0]
 
     nmr_files, deg_files = listing(nmr), listing(deg)
+    if matrix is None:
+        matrix = "root" if 4 * len(nmr_files) * len(deg_files) <= ROOT_MATRIX_LIMIT_BYTES else "local"
+    if matrix == "local" and results_path is None:
+        raise Exception("row-sharded scores need results_path (every rank writes its rows there)")
 
-    def embed_files(files):
-        def fn(idx):
-            waves = [nomad.load_processing(files[i]).reshape(-1) for i in idx]
-            return torch.from_numpy(nomad.embed_waves(waves)).to(device)
-        return fn
-
+    # windowed, length-bucketed, device-ingest loader of Nomad.get_embeddings_csv, on this rank's files only
+    embed_files = lambda files: (lambda idx: nomad.embed_files([files[i] for i in idx]))
     cost = lambda files: [float(os.path.getsize(f)) for f in files]
-    nmr_emb = sharded_embeddings(cost(nmr_files), embed_files(nmr_files), 256, device, group)
-    res = sharded_scores(cost(deg_files), embed_files(deg_files), nmr_emb,
-                         lambda a, b, wm: nomad.engine.cdist_mean(a, b, wm), device, group)
+    res = score_sharded(cost(nmr_files), embed_files(nmr_files), cost(deg_files), embed_files(deg_files),
+                        lambda a, b, wm: nomad.engine.cdist_mean(a, b, wm), device, group, matrix)
+    if matrix == "local":
+        rows = res["local_rows"]
+        from . import _lib
+        stems = [x.split('/')[-1].split('.')[0] for x in deg_files]
+        _lib.write_scores_csv(os.path.join(results_path, f"nomad_scores.rank{rank}.csv"), 'Test File',
+                              [stems[i] for i in rows], [x.split('/')[-1].split('.')[0] for x in nmr_files],
+                              res["local_dm"].cpu().numpy().astype(np.float64).reshape(len(rows), len(nmr_files)))
     if rank != 0:
         return None
-    dm, mean, _ = res
-    return nomad.write_results(deg_files, nmr_files, dm, mean, results_path)
+    mean = res["mean"].cpu().numpy()
+    if matrix == "local":
+        return nomad.write_results(deg_files, nmr_files, None, mean, results_path)
+    return nomad.write_results(deg_files, nmr_files, res["dm"].cpu().numpy().astype(np.float64), mean, results_path)

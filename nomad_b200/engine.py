@@ -140,6 +140,43 @@ class Engine:
                        "nomad_b200_embed_host")
         return emb_host
 
+    def score_packed(self, wav: torch.Tensor, offsets: np.ndarray, nmr: torch.Tensor, want_matrix: bool = True):
+        """One batch of ``Nomad.predict`` on device-resident data: -> (emb (B, 256), dm (B, m) | None, mean (B,) fp64)."""
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous()
+        assert nmr.is_cuda and nmr.dtype == torch.float32 and nmr.is_contiguous() and nmr.shape[1] == EMB_DIM
+        B, m = len(offsets) - 1, nmr.shape[0]
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        need = self.lib.nomad_b200_score_workspace_bytes(off_p, B, m)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        wp, wbytes = self._aligned(self.workspace(need))
+        emb = torch.empty((B, EMB_DIM), dtype=torch.float32, device=self.device)
+        dm = torch.empty((B, m), dtype=torch.float32, device=self.device) if want_matrix else None
+        mean = torch.empty((B,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_score(self.handle, _ptr(wav), off_p, B, _ptr(nmr), m, _ptr(emb), _ptr(dm),
+                                                 _ptr(mean), wp, wbytes, _stream_ptr()), "nomad_b200_score")
+        return emb, dm, mean
+
+    def score_host(self, wav_host: np.ndarray, offsets: np.ndarray, nmr: torch.Tensor, emb_host: Optional[np.ndarray],
+                   dm_host: Optional[np.ndarray], mean_host: np.ndarray):
+        """Same with HOST waveforms in and HOST results out (H2D + compute + D2H + sync inside the C call)."""
+        assert wav_host.dtype == np.float32 and wav_host.flags.c_contiguous and mean_host.dtype == np.float64
+        assert nmr.is_cuda and nmr.dtype == torch.float32 and nmr.is_contiguous() and nmr.shape[1] == EMB_DIM
+        B, m = len(offsets) - 1, nmr.shape[0]
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
+        need = self.lib.nomad_b200_score_workspace_bytes(off_p, B, m)
+        if need == 0:
+            raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
+        wp, wbytes = self._aligned(self.workspace(need))
+        hp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_score_host(self.handle, hp(wav_host), off_p, B, _ptr(nmr), m, hp(emb_host),
+                                                      hp(dm_host), hp(mean_host), wp, wbytes, _stream_ptr()),
+                       "nomad_b200_score_host")
+
     # ------------------------------------------------------------------ ingest
     def ingest_pcm16(self, pcm: np.ndarray, sr: int, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
         """``load_processing`` on the device: (n_frames, channels) or (n_frames,) int16 HOST samples at ``sr`` ->
@@ -207,6 +244,10 @@ class Engine:
         """(n, 256), (m, 256) fp32 CUDA -> ((n, m) fp32 | None, (n,) fp64 row means)."""
         deg = deg.to(self.device, torch.float32).contiguous()
         nmr = nmr.to(self.device, torch.float32).contiguous()
+        if deg.dim() != 2 or nmr.dim() != 2 or deg.shape[1] != EMB_DIM or nmr.shape[1] != EMB_DIM:
+            # the kernels address rows of exactly 256 floats (nomad.py:55 EMB_DIM); anything else would be read misaligned
+            raise ValueError(f"cdist_mean needs (n, {EMB_DIM}) and (m, {EMB_DIM}) embeddings, got {tuple(deg.shape)} "
+                             f"and {tuple(nmr.shape)}")
         n, m = deg.shape[0], nmr.shape[0]
         dm = torch.empty((n, m), dtype=torch.float32, device=self.device) if want_matrix else None
         mean = torch.empty((n,), dtype=torch.float64, device=self.device)

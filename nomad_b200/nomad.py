@@ -213,10 +213,12 @@ class Nomad():
         test_files = [x.split('/')[-1].split('.')[0] for x in test_index]
         df_avg_nomad = pd.DataFrame({'Test File': test_files, 'NOMAD': avg_nomad}).set_index('Test File').round(3)
 
-        df_dm = pd.DataFrame(distance_matrix).round(3)
-        df_dm['Test File'] = test_files
-        df_dm.set_index('Test File', inplace=True)
-        df_dm.columns = [x.split('/')[-1].split('.')[0] for x in nmr_index]
+        df_dm = None
+        if distance_matrix is not None:  # None: the rows were written per rank (dist.predict_sharded, matrix='local')
+            df_dm = pd.DataFrame(distance_matrix).round(3)
+            df_dm['Test File'] = test_files
+            df_dm.set_index('Test File', inplace=True)
+            df_dm.columns = [x.split('/')[-1].split('.')[0] for x in nmr_index]
 
         # Save results (nomad.py:122-139)
         if results_path == None:
@@ -238,8 +240,9 @@ class Nomad():
         # multi-threaded formatter from the unrounded values: pandas takes minutes on a 1e5 x 1e3 frame
         from . import _lib
         _lib.write_scores_csv(results_avg_path, 'Test File', test_files, ['NOMAD'], np.asarray(avg_nomad, dtype=np.float64))
-        _lib.write_scores_csv(results_scores_path, 'Test File', test_files, list(df_dm.columns),
-                              np.asarray(distance_matrix, dtype=np.float64))
+        if df_dm is not None:
+            _lib.write_scores_csv(results_scores_path, 'Test File', test_files, list(df_dm.columns),
+                                  np.asarray(distance_matrix, dtype=np.float64))
         return df_avg_nomad, df_dm
 
     def pairwise(self, test_embeddings, nmr_embeddings):
@@ -248,6 +251,8 @@ class Nomad():
         ne = np.ascontiguousarray(np.asarray(nmr_embeddings, dtype=np.float32))
         if te.ndim != 2 or ne.ndim != 2 or te.shape[1] != ne.shape[1]:
             raise ValueError('XA and XB must have the same number of columns (i.e. feature dimension.)')
+        if te.shape[1] != EMB_DIM:
+            raise ValueError(f'NOMAD embeddings have {EMB_DIM} columns, got {te.shape[1]} (an extra csv column?)')
         dm, mean = self.engine.cdist_mean(torch.from_numpy(te), torch.from_numpy(ne))
         return dm.cpu().numpy().astype(np.float64), mean.cpu().numpy()
 
@@ -283,17 +288,16 @@ class Nomad():
             out[torch.as_tensor(idx, device=self.engine.device)] = emb
         return out.cpu().numpy()
 
-    # Function that extract NOMAD embeddings and store them in a DataFrame (nomad.py:166-189)
-    def get_embeddings_csv(self, model, file_names, root=False):
-        """Per-file loop of the reference, restructured for throughput: files are read in windows of
-        ``self.window_files`` (bounded memory for 100 k-file corpora), every window is length-bucketed into batches,
-        and the GPU works on window k while the host reads window k + 1 (no per-batch synchronisation)."""
-        file_names_arr = np.array(file_names)
-        n_files = len(file_names_arr)
+    def embed_files(self, filepaths: Sequence, root=False) -> torch.Tensor:
+        """The reference's per-file loop (``nomad.py:172-186``) restructured for throughput -> (n, 256) CUDA tensor in
+        input order.  Files are read in windows of ``self.window_files`` (bounded memory for 100 k-file corpora),
+        every window is length-bucketed into batches, and the GPU works on window k while the host reads window
+        k + 1 (no per-batch synchronisation; the returned tensor may still be being computed)."""
+        n_files = len(filepaths)
         parts = []
         for w0 in range(0, n_files, self.window_files):
             waves = []
-            for filename_anchor in file_names_arr[w0:w0 + self.window_files]:
+            for filename_anchor in filepaths[w0:w0 + self.window_files]:
                 if root:
                     filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
                 else:
@@ -311,7 +315,13 @@ class Nomad():
             for idx in plan_batches(lengths, self.max_batch_samples):
                 dev_out[torch.as_tensor(idx, device=self.engine.device)] = self.engine.embed([waves[i] for i in idx])
             parts.append(dev_out)  # still being computed; the host goes on reading the next window
-        embeddings = (torch.cat(parts).cpu().numpy() if parts else np.zeros((0, EMB_DIM), dtype=np.float32))
+        if not parts:
+            return torch.zeros((0, EMB_DIM), dtype=torch.float32, device=self.engine.device)
+        return torch.cat(parts) if len(parts) > 1 else parts[0]
+
+    # Function that extract NOMAD embeddings and store them in a DataFrame (nomad.py:166-189)
+    def get_embeddings_csv(self, model, file_names, root=False):
+        embeddings = self.embed_files(np.array(file_names), root).cpu().numpy()
         embeddings = pd.DataFrame(embeddings)
         df_emb = pd.concat([file_names.reset_index(), embeddings], axis=1).drop('index', axis=1)
         return df_emb
