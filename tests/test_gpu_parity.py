@@ -98,23 +98,27 @@ def test_gemm_tcgen05_vs_torch_and_simt(M, N, K, lda, wrap, batch, flags):
 
 
 # ------------------------------------------------------------------------------- golden fixtures
-def test_layers_and_embeddings_small_batch(engine, golden_dir):
+def test_layers_and_embeddings_small_batch(engine, golden_dir, record):
     g = np.load(os.path.join(golden_dir, "ref_small.npz"))
     wav = torch.from_numpy(g["wav_b"]).cuda()
     layers, _ = engine.layers(wav)
     layers = layers.cpu().numpy()
     assert layers.shape == g["layers_b"].shape
-    for l in range(12):
-        assert np.abs(layers[l] - g["layers_b"][l]).max() <= LAYER_TOL, l
+    errs = [float(np.abs(layers[l] - g["layers_b"][l]).max()) for l in range(12)]
     emb = engine.embed([wav[i] for i in range(wav.shape[0])]).cpu().numpy()
+    record("layers_and_embeddings_small_batch", layer_max_abs_err=max(errs), layer0_err=errs[0], layer11_err=errs[11],
+           layer_abs_max=float(np.abs(g["layers_b"]).max()), emb_max_abs_err=float(np.abs(emb - g["emb_b"]).max()))
+    for l in range(12):
+        assert errs[l] <= LAYER_TOL, l
     assert np.abs(emb - g["emb_b"]).max() <= EMB_TOL
     np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
 
 
-def test_variable_length_batch_equals_per_file_reference(engine, golden_dir):
+def test_variable_length_batch_equals_per_file_reference(engine, golden_dir, record):
     g = np.load(os.path.join(golden_dir, "ref_small.npz"))
     waves = _split(torch.from_numpy(g["wav_v"]), g["lens"].tolist())
     emb = engine.embed(waves).cpu().numpy()
+    record("variable_length_batch", emb_max_abs_err=float(np.abs(emb - g["emb_v"]).max()))
     assert np.abs(emb - g["emb_v"]).max() <= EMB_TOL
     # batch composition must not matter: each utterance alone gives the same bits
     for i in (0, 3, 7):
@@ -334,7 +338,7 @@ def test_cdist_full_size_properties(engine):
 
 
 # ------------------------------------------------------------------------------ full-size embedding
-def test_full_size_batch_properties(engine, state_dict):
+def test_full_size_batch_properties(engine, state_dict, record):
     """BASELINE config 2 (256 x 4 s): unit norm, finite, batch-composition invariance, and two
     utterances against the oracle."""
     from oracle import w2v_oracle as O
@@ -349,13 +353,14 @@ def test_full_size_batch_properties(engine, state_dict):
     np.testing.assert_array_equal(sub, e[[5, 200]])
     with torch.no_grad():
         ref = O.embed(state_dict, wav[[5, 200]]).numpy()
+    record("full_size_batch_256x4s", emb_max_abs_err=float(np.abs(sub - ref).max()))
     assert np.abs(sub - ref).max() <= EMB_TOL
     # host-buffer entry point (H2D + D2H inside) returns the same bits
     host = engine.embed_host(np.ascontiguousarray(wav[:8].numpy().reshape(-1)), np.arange(9, dtype=np.int64) * N)
     np.testing.assert_array_equal(host, e[:8])
 
 
-def test_mixed_long_short_batch_against_oracle(engine, state_dict):
+def test_mixed_long_short_batch_against_oracle(engine, state_dict, record):
     """Config-3 style ragged batch (1-20 s) incl. lengths straddling the 64-row / 128-row tile edges."""
     from oracle import w2v_oracle as O
     g = torch.Generator().manual_seed(3)
@@ -363,6 +368,7 @@ def test_mixed_long_short_batch_against_oracle(engine, state_dict):
     waves = [0.1 * torch.randn(n, generator=g) for n in lens]
     emb = engine.embed(waves).cpu().numpy()
     ref = O.embed_each(state_dict, waves).numpy()
+    record("mixed_long_short_batch", emb_max_abs_err=float(np.abs(emb - ref).max()))
     assert np.abs(emb - ref).max() <= EMB_TOL
     # host-buffer entry point: the H2D copy is pipelined in utterance groups against the front end; same bits,
     # also for fewer utterances than copy groups
@@ -409,7 +415,7 @@ def _loss_nomad(state_dict, golden_dir, fgm):
 
 
 @pytest.mark.parametrize("fgm", [1.0, 0.1])
-def test_loss_value_and_gradient_against_reference(state_dict, golden_dir, fgm):
+def test_loss_value_and_gradient_against_reference(state_dict, golden_dir, fgm, record):
     """``nomad.forward(estimate, clean)`` + ``loss.backward()`` (nomad_loss_test.py:69-73) vs the reference run.
     Tolerances: loss 2e-3 relative; gradient max error <= 1 % of max|grad|, cosine >= 0.9999."""
     nomad, g = _loss_nomad(state_dict, golden_dir, fgm)
@@ -422,8 +428,10 @@ def test_loss_value_and_gradient_against_reference(state_dict, golden_dir, fgm):
     assert abs(loss.item() - ref_l) <= 2e-3 * ref_l
     got = est.grad.cpu().numpy() / 3.0
     assert got.shape == ref_g.shape
-    assert np.abs(got - ref_g).max() <= 1e-2 * np.abs(ref_g).max()
     cos = float((got * ref_g).sum() / (np.linalg.norm(got) * np.linalg.norm(ref_g)))
+    record("loss_vs_reference_fixture", fgm=fgm, loss_rel_err=abs(loss.item() - ref_l) / ref_l,
+           grad_max_err_over_max=float(np.abs(got - ref_g).max() / np.abs(ref_g).max()), grad_cosine=cos)
+    assert np.abs(got - ref_g).max() <= 1e-2 * np.abs(ref_g).max()
     assert cos >= 0.9999
     # no-grad call returns the same value and needs no backward workspace
     with torch.no_grad():

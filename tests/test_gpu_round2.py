@@ -1,0 +1,176 @@
+"""Round-2 parity tests: the one-call scoring entry points, deterministic row means, the loss at BASELINE
+configs[3] size (32 x 2 s), and stress cases for the 16-bit operand path (large activations, narrow-band conv0
+channels on DC-offset input).  Every test records the error it ACHIEVED (conftest ``record``)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+EMB_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def engine(state_dict):
+    from nomad_b200.engine import Engine
+    return Engine(state_dict, 0)
+
+
+# ------------------------------------------------------------------------------ nomad_b200_score / _score_host
+def test_score_entry_points_equal_embed_plus_cdist(engine):
+    g = torch.Generator().manual_seed(21)
+    lens = [16000, 48000, 20481, 64000, 9000]
+    waves = [0.1 * torch.randn(n, generator=g) for n in lens]
+    nmr = torch.nn.functional.normalize(torch.randn(300, 256, generator=g), dim=1).cuda()
+    off = engine.offsets(lens)
+    flat = torch.cat(waves)
+    emb0 = engine.embed(waves)
+    dm0, mean0 = engine.cdist_mean(emb0, nmr)
+    emb, dm, mean = engine.score_packed(flat.cuda(), off, nmr)
+    assert torch.equal(emb, emb0) and torch.equal(dm, dm0) and torch.equal(mean, mean0)
+    _, none_dm, mean2 = engine.score_packed(flat.cuda(), off, nmr, want_matrix=False)
+    assert none_dm is None and torch.equal(mean2, mean0)
+    eh, dh, mh = np.empty((5, 256), np.float32), np.empty((5, 300), np.float32), np.empty((5,), np.float64)
+    engine.score_host(np.ascontiguousarray(flat.numpy()), off, nmr, eh, dh, mh)
+    np.testing.assert_array_equal(eh, emb0.cpu().numpy())
+    np.testing.assert_array_equal(dh, dm0.cpu().numpy())
+    np.testing.assert_array_equal(mh, mean0.cpu().numpy())
+    mh2 = np.empty((5,), np.float64)
+    engine.score_host(np.ascontiguousarray(flat.numpy()), off, nmr, None, None, mh2)   # means only
+    np.testing.assert_array_equal(mh2, mh)
+
+
+# ------------------------------------------------------------------------------------------------- cdist
+def test_cdist_row_means_are_bit_identical_from_run_to_run(engine, record):
+    """Row sums are per-(column group, row) partials added in a fixed order (no atomics): nomad_avg.csv cannot flip a
+    third decimal between runs."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.nn.functional.normalize(torch.randn(50_000, 256, device="cuda", generator=g), dim=1)
+    for m in (1000, 899, 8192, 40):
+        b = torch.nn.functional.normalize(torch.randn(m, 256, device="cuda", generator=g), dim=1)
+        n = 50_000 if m != 40 else 1000   # 1000 x 40 takes the fp32 direct kernel
+        runs = [engine.cdist_mean(a[:n], b, want_matrix=(i % 2 == 0))[1].clone() for i in range(6)]
+        for r in runs[1:]:
+            assert torch.equal(r, runs[0]), m
+        ref = torch.cdist(a[:2000].double(), b.double()).mean(1)
+        err = float((runs[0][:2000] - ref).abs().max())
+        record("cdist_row_mean", n=n, m=m, max_abs_err=err)
+        assert err <= 1e-5
+
+
+@pytest.mark.parametrize("m", [1, 3, 4, 15, 16, 17])
+def test_cdist_many_rows_few_nmr(engine, m, record):
+    """Tensor-core path (n * m >= 65536) with fewer NMR rows than one MMA column group (e.g. the 4 bundled NMR files
+    against a corpus)."""
+    g = torch.Generator(device="cuda").manual_seed(m)
+    n = 70_000
+    a = torch.nn.functional.normalize(torch.randn(n, 256, device="cuda", generator=g), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(m, 256, device="cuda", generator=g), dim=1)
+    dm, mean = engine.cdist_mean(a, b)
+    ref = torch.cdist(a.double(), b.double())
+    e1, e2 = float((dm.double() - ref).abs().max()), float((mean - ref.mean(1)).abs().max())
+    record("cdist_few_nmr", n=n, m=m, dm_max_abs_err=e1, mean_max_abs_err=e2)
+    assert e1 <= 1e-5 and e2 <= 1e-5
+
+
+def test_cdist_empty_nmr_and_wrong_width(engine):
+    a = torch.nn.functional.normalize(torch.randn(5, 256), dim=1).cuda()
+    dm, mean = engine.cdist_mean(a, torch.zeros(0, 256).cuda())
+    assert dm.shape == (5, 0) and bool(torch.isnan(mean).all())     # np.mean of an empty row is NaN
+    with pytest.raises(ValueError):
+        engine.cdist_mean(torch.zeros(5, 257), torch.zeros(3, 257))
+    with pytest.raises(ValueError):
+        engine.cdist_mean(torch.zeros(5, 256), torch.zeros(3, 255))
+
+
+# -------------------------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("fgm", [0.1, 1.0])
+def test_loss_at_baseline_config3_size(state_dict, fgm, record):
+    """``nomad.forward`` + backward at BASELINE configs[3] (32 x 2 s estimate/clean pairs, T = 99) against the oracle's
+    autograd on the host.  Tolerances (achieved values are recorded): loss 1e-3 relative; gradient max error <= 0.5 %
+    of max|grad|, cosine >= 0.99995, per-utterance relative L2 error <= 1 %."""
+    from nomad_b200.nomad import Nomad
+    from oracle import w2v_oracle as O
+    B, N = 32, 32000
+    g = torch.Generator().manual_seed(17)
+    clean = 0.1 * torch.randn(B, 1, N, generator=g)
+    est = clean + 0.03 * torch.randn(B, 1, N, generator=g)       # an enhancement output: close to the target
+    est[B // 2:] = 0.1 * torch.randn(B - B // 2, 1, N, generator=g)  # and unrelated signals
+    nomad = Nomad(state_dict=state_dict, feature_grad_mult=fgm)
+    lin = nomad.lossnet_layers.embedding_layer[1]
+    e_dev = est.cuda().requires_grad_(True)
+    loss = nomad.forward(e_dev, clean.cuda())
+    loss.backward()
+    got = e_dev.grad.cpu().numpy().reshape(B, N)
+    torch.set_num_threads(os.cpu_count() or 1)
+    e_cpu = est.clone().requires_grad_(True)
+    lo = O.nomad_forward(state_dict, lin.weight.detach().cpu(), lin.bias.detach().cpu(), e_cpu, clean, feature_grad_mult=fgm)
+    lo.backward()
+    ref = e_cpu.grad.numpy().reshape(B, N)
+    rel_loss = abs(loss.item() - lo.item()) / lo.item()
+    max_rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+    cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref)))
+    row_rel = float((np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
+    record("loss_c4", fgm=fgm, loss=loss.item(), loss_rel_err=rel_loss, grad_max_err_over_max=max_rel, grad_cosine=cos,
+           grad_worst_row_rel_l2=row_rel)
+    assert rel_loss <= 1e-3
+    assert max_rel <= 5e-3 and cos >= 0.99995 and row_rel <= 1e-2
+
+
+# ------------------------------------------------------------------------------------- 16-bit operand stress
+def test_large_activation_weights_against_oracle(record):
+    """fp16 operands saturate at 65504 and carry 11 bits: a checkpoint with outlier LayerNorm gains (x16 on a few
+    channels, as trained wav2vec 2.0 models have), 6x larger FFN pre-activations and 4x larger attention logits must
+    still land within the tolerance of the fp32 reference arithmetic."""
+    from nomad_b200.engine import Engine
+    from nomad_b200.weights import random_state_dict
+    from oracle import w2v_oracle as O
+    sd = random_state_dict(77)
+    P = "ssl_model.encoder.layers."
+    for l in range(12):
+        for ln in ("self_attn_layer_norm", "final_layer_norm"):
+            sd[f"{P}{l}.{ln}.weight"][[5, 100 + l, 700]] *= 16.0
+        sd[f"{P}{l}.fc1.weight"] *= 6.0
+        sd[f"{P}{l}.fc2.weight"] /= 6.0
+        sd[f"{P}{l}.self_attn.q_proj.weight"] *= 2.0
+        sd[f"{P}{l}.self_attn.k_proj.weight"] *= 2.0
+    sd["ssl_model.encoder.layer_norm.weight"][[5, 333]] *= 16.0
+    eng = Engine(sd, 0)
+    g = torch.Generator().manual_seed(2)
+    waves = [1.0 * torch.randn(n, generator=g).clamp(-1, 1) for n in (32000, 16000, 50000)]   # full-scale audio
+    emb = eng.embed(waves).cpu().numpy()
+    with torch.no_grad():
+        ref = O.embed_each(sd, waves, dtype=torch.float64).float().numpy()
+    err = float(np.abs(emb - ref).max())
+    record("stress_large_activations", emb_max_abs_err=err)
+    assert np.isfinite(emb).all() and err <= 2e-3
+
+
+def test_narrow_band_conv0_channels_on_dc_offset_input(record):
+    """GroupNorm statistics come from quadratic forms of waveform sums (frontend.cu): difference filters on a
+    low-frequency tone with a DC offset cancel most leading digits of those sums -- fp64 accumulation keeps the
+    variance exact.  Compared with the fp64 oracle."""
+    from nomad_b200.engine import Engine
+    from nomad_b200.weights import random_state_dict
+    from oracle import w2v_oracle as O
+    sd = random_state_dict(5)
+    w0 = sd["ssl_model.feature_extractor.conv_layers.0.0.weight"]
+    w0[0, 0] = torch.tensor([1., -1, 0, 0, 0, 0, 0, 0, 0, 0])
+    w0[1, 0] = torch.tensor([1., -2, 1, 0, 0, 0, 0, 0, 0, 0])
+    w0[2, 0] = torch.tensor([0, 0, 0, 1., -2, 1, 0, 0, 0, 0]) * 3.0
+    w0[3, 0] = torch.full((10,), 0.1)                                   # pure low-pass: output ~ the DC offset
+    w0[4, 0] = torch.tensor([1., -1, 1, -1, 1, -1, 1, -1, 1, -1]) * 0.5  # Nyquist band-pass
+    eng = Engine(sd, 0)
+    g = torch.Generator().manual_seed(8)
+    waves = []
+    for n, f0, dc in ((48000, 200.0, 0.3), (20000, 90.0, -0.5), (64000, 440.0, 0.05)):
+        t = torch.arange(n, dtype=torch.float64) / 16000.0
+        waves.append((dc + 0.4 * torch.sin(2 * np.pi * f0 * t) + 0.01 * torch.randn(n, generator=g, dtype=torch.float64)).float())
+    emb = eng.embed(waves).cpu().numpy()
+    with torch.no_grad():
+        ref = O.embed_each(sd, waves, dtype=torch.float64).float().numpy()
+    err = float(np.abs(emb - ref).max())
+    record("narrow_band_conv0_dc_offset", emb_max_abs_err=err)
+    assert err <= EMB_TOL
