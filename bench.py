@@ -381,14 +381,14 @@ def run_ours(args):
     dm_pin = torch.empty((CLIPS, NMR_M), dtype=torch.float32).pin_memory()
     mean_pin = torch.empty((CLIPS,), dtype=torch.float64).pin_memory()
     emb_pin_np, dm_pin_np, mean_pin_np = emb_pin.numpy(), dm_pin.numpy(), mean_pin.numpy()
-    row_shards = [list(range(r * CLIPS, (r + 1) * CLIPS)) for r in range(world)]
+    row_counts = [CLIPS] * world   # rank r owns global rows [r * CLIPS, (r + 1) * CLIPS): rank order = listing order
     last = {}
 
     def step_dev():
         emb, dm, mean = eng.score_packed(wav_dev, off, nmr_emb)
         if world > 1:  # the path's exchange: this rank's rows of the result go to rank 0
-            last["mean"] = nd.gather_shards_to_root(mean.reshape(-1, 1), row_shards)
-            last["dm"] = nd.gather_shards_to_root(dm, row_shards)
+            got = nd.gather_rows_to_root([dm, mean.reshape(-1, 1)], row_counts)  # one NCCL group call
+            last["dm"], last["mean"] = got if got is not None else (None, None)
         else:
             last["mean"], last["dm"] = mean, dm
         last["emb"] = emb
@@ -422,13 +422,12 @@ def run_ours(args):
         emb, dm, mean = eng.score_packed(wav_dev, off, nmr_emb)
 
         def xchg():
-            nd.gather_shards_to_root(mean.reshape(-1, 1), row_shards)
-            nd.gather_shards_to_root(dm, row_shards)
+            nd.gather_rows_to_root([dm, mean.reshape(-1, 1)], row_counts)
         exchange_ms = timed(xchg, 20) / 20
 
     # ------------------------------------------------------------------ configs[4] slice: fixed global PAIR_N x PAIR_M
-    pair_shards = [list(range(r * PAIR_N // world, (r + 1) * PAIR_N // world)) for r in range(world)]
-    n_loc = len(pair_shards[rank])
+    pair_counts = [(r + 1) * PAIR_N // world - r * PAIR_N // world for r in range(world)]  # contiguous row ranges
+    n_loc = pair_counts[rank]
     gq = torch.Generator().manual_seed(100 + rank)
     deg_e = torch.nn.functional.normalize(torch.randn(n_loc, 256, generator=gq), dim=1).to(dev)
     nmr_e = torch.nn.functional.normalize(torch.randn(PAIR_M, 256, generator=torch.Generator().manual_seed(5)), dim=1).to(dev)
@@ -436,7 +435,7 @@ def run_ours(args):
     def pair_step(want_matrix):
         def fn():
             _dm, mean = eng.cdist_mean(deg_e, nmr_e, want_matrix=want_matrix)   # matrix rows stay with the rank
-            nd.gather_shards_to_root(mean.reshape(-1, 1), pair_shards)           # means to rank 0
+            nd.gather_rows_to_root(mean.reshape(-1, 1), pair_counts)             # means to rank 0
         return fn
     for _ in range(3):
         pair_step(True)()
@@ -541,6 +540,8 @@ def run_ours(args):
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.dup2(2, 1)  # NCCL_DEBUG=INFO logs communicator teardown to stdout: keep the ONE JSON line clean
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -87,38 +87,49 @@ def all_gather_shards(local: torch.Tensor, shards: List[List[int]], group=None, 
     return pend if async_op else pend.result()
 
 
-def gather_shards_to_root(local: torch.Tensor, shards: List[List[int]], group=None) -> Optional[torch.Tensor]:
-    """Send every rank's row block to rank 0 only (exact sizes, one batch of point-to-point operations in the group's
-    communicator).  Rank 0 returns the rows in listing order (same device); other ranks return ``None``."""
+def gather_rows_to_root(local, counts: Sequence[int], group=None):
+    """Send every rank's row block (``counts[r]`` rows on rank r) to rank 0 only: exact sizes, ONE batch of
+    point-to-point operations in the group's communicator (one NCCL group call, also for several tensors).  ``local``
+    is a tensor or a list of tensors with the same row count (e.g. matrix rows + their means).  Rank 0 returns the
+    blocks concatenated in RANK order (same device); other ranks return ``None``."""
     rank, world = _world(group)
-    assert local.shape[0] == len(shards[rank])
+    many = isinstance(local, (list, tuple))
+    locs = [t.contiguous() for t in (local if many else [local])]
+    assert all(t.shape[0] == counts[rank] for t in locs)
     if world == 1:
-        return local.index_select(0, _listing_index(shards, 0, local.device)) if local.shape[0] else local
-    local = local.contiguous()
+        return locs if many else locs[0]
+    root = dist.get_global_rank(group, 0) if group is not None else 0
     if rank != 0:
-        if local.shape[0]:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dist.get_global_rank(group, 0) if group else 0,
-                                                        group=group)]):
+        if counts[rank]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, root, group=group) for t in locs]):
                 w.wait()
         return None
-    n = sum(len(s) for s in shards)
-    buf = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    starts = np.concatenate([[0], np.cumsum([len(s) for s in shards])]).astype(np.int64)
-    buf[: local.shape[0]] = local
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    bufs = [torch.empty((int(starts[-1]),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in locs]
     ops = []
+    for t, buf in zip(locs, bufs):
+        buf[: t.shape[0]] = t
     for r in range(1, world):
-        if shards[r]:
-            peer = dist.get_global_rank(group, r) if group else r
-            ops.append(dist.P2POp(dist.irecv, buf[starts[r]: starts[r + 1]], peer, group=group))
+        if counts[r]:
+            peer = dist.get_global_rank(group, r) if group is not None else r
+            ops += [dist.P2POp(dist.irecv, buf[starts[r]: starts[r + 1]], peer, group=group) for buf in bufs]
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    # buf stores shard r at rows [starts[r], starts[r+1]): listing position i -> its row
-    src = np.empty((n,), dtype=np.int64)
+    return bufs if many else bufs[0]
+
+
+def gather_shards_to_root(local: torch.Tensor, shards: List[List[int]], group=None) -> Optional[torch.Tensor]:
+    """``gather_rows_to_root`` + restoring listing order: rank 0 returns the rows of all shards in listing order."""
+    got = gather_rows_to_root(local, [len(s) for s in shards], group)
+    if got is None or got.shape[0] == 0:
+        return got
+    starts = np.concatenate([[0], np.cumsum([len(s) for s in shards])]).astype(np.int64)
+    src = np.empty((int(starts[-1]),), dtype=np.int64)
     for r, s in enumerate(shards):
         if s:
             src[np.asarray(s, dtype=np.int64)] = starts[r] + np.arange(len(s), dtype=np.int64)
-    return buf.index_select(0, torch.from_numpy(src).to(buf.device))
+    return got.index_select(0, torch.from_numpy(src).to(got.device))
 
 
 def sharded_embeddings(costs: Sequence[float], embed: Callable[[List[int]], torch.Tensor], dim: int,

@@ -13,7 +13,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 EMB_TOL = 1e-3
-LAYER_TOL = 2.5e-2  # per-element, layer outputs have |x| up to ~4 (fp16 operand rounding accumulates over 12 layers)
+LAYER_TOL = 1e-2  # per-element, layer outputs have |x| up to ~4.6; achieved 5.8e-3 (profiles/r02_parity_achieved.jsonl)
 
 
 @pytest.fixture(scope="module")
@@ -417,7 +417,8 @@ def _loss_nomad(state_dict, golden_dir, fgm):
 @pytest.mark.parametrize("fgm", [1.0, 0.1])
 def test_loss_value_and_gradient_against_reference(state_dict, golden_dir, fgm, record):
     """``nomad.forward(estimate, clean)`` + ``loss.backward()`` (nomad_loss_test.py:69-73) vs the reference run.
-    Tolerances: loss 2e-3 relative; gradient max error <= 1 % of max|grad|, cosine >= 0.9999."""
+    Tolerances: loss 1e-3 relative; gradient max error <= 0.6 % of max|grad|, cosine >= 0.99998 (achieved: 1.6e-4,
+    0.33 %, 0.999993 -- profiles/r02_parity_achieved.jsonl)."""
     nomad, g = _loss_nomad(state_dict, golden_dir, fgm)
     est = torch.from_numpy(g["est"]).cuda().requires_grad_(True)
     clean = torch.from_numpy(g["clean"]).cuda()
@@ -425,14 +426,14 @@ def test_loss_value_and_gradient_against_reference(state_dict, golden_dir, fgm, 
     assert loss.dim() == 0 and loss.requires_grad
     (3.0 * loss).backward()
     ref_l, ref_g = float(g[f"loss_fgm{fgm}"]), g[f"grad_fgm{fgm}"]
-    assert abs(loss.item() - ref_l) <= 2e-3 * ref_l
+    assert abs(loss.item() - ref_l) <= 1e-3 * ref_l
     got = est.grad.cpu().numpy() / 3.0
     assert got.shape == ref_g.shape
     cos = float((got * ref_g).sum() / (np.linalg.norm(got) * np.linalg.norm(ref_g)))
     record("loss_vs_reference_fixture", fgm=fgm, loss_rel_err=abs(loss.item() - ref_l) / ref_l,
            grad_max_err_over_max=float(np.abs(got - ref_g).max() / np.abs(ref_g).max()), grad_cosine=cos)
-    assert np.abs(got - ref_g).max() <= 1e-2 * np.abs(ref_g).max()
-    assert cos >= 0.9999
+    assert np.abs(got - ref_g).max() <= 6e-3 * np.abs(ref_g).max()
+    assert cos >= 0.99998
     # no-grad call returns the same value and needs no backward workspace
     with torch.no_grad():
         l2 = nomad.forward(est.detach(), clean)

