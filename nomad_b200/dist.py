@@ -119,17 +119,23 @@ def gather_rows_to_root(local, counts: Sequence[int], group=None):
     return bufs if many else bufs[0]
 
 
-def gather_shards_to_root(local: torch.Tensor, shards: List[List[int]], group=None) -> Optional[torch.Tensor]:
-    """``gather_rows_to_root`` + restoring listing order: rank 0 returns the rows of all shards in listing order."""
+def gather_shards_to_root(local, shards: List[List[int]], group=None):
+    """``gather_rows_to_root`` + restoring listing order: rank 0 returns the rows of all shards in listing order
+    (a tensor, or a list of tensors when ``local`` is a list)."""
     got = gather_rows_to_root(local, [len(s) for s in shards], group)
-    if got is None or got.shape[0] == 0:
-        return got
-    starts = np.concatenate([[0], np.cumsum([len(s) for s in shards])]).astype(np.int64)
-    src = np.empty((int(starts[-1]),), dtype=np.int64)
-    for r, s in enumerate(shards):
-        if s:
-            src[np.asarray(s, dtype=np.int64)] = starts[r] + np.arange(len(s), dtype=np.int64)
-    return got.index_select(0, torch.from_numpy(src).to(got.device))
+    if got is None:
+        return None
+    many = isinstance(got, (list, tuple))
+    gots = list(got) if many else [got]
+    if gots[0].shape[0]:
+        starts = np.concatenate([[0], np.cumsum([len(s) for s in shards])]).astype(np.int64)
+        src = np.empty((int(starts[-1]),), dtype=np.int64)
+        for r, s in enumerate(shards):
+            if s:
+                src[np.asarray(s, dtype=np.int64)] = starts[r] + np.arange(len(s), dtype=np.int64)
+        idx = torch.from_numpy(src).to(gots[0].device)
+        gots = [g.index_select(0, idx) for g in gots]
+    return gots if many else gots[0]
 
 
 def sharded_embeddings(costs: Sequence[float], embed: Callable[[List[int]], torch.Tensor], dim: int,
@@ -165,11 +171,19 @@ def sharded_scores(deg_costs: Sequence[float], embed: Callable[[List[int]], torc
         dm = torch.zeros((0, M), dtype=torch.float32, device=device) if matrix != "none" else None
         mean = torch.zeros((0,), dtype=torch.float64, device=device)
     out = {"local_rows": mine, "local_mean": mean, "local_dm": dm if matrix == "local" else None, "nmr": nmr_emb}
-    got = gather_shards_to_root(mean.reshape(-1, 1).to(torch.float64), shards, group)
-    out["mean"] = got.reshape(-1) if got is not None else None
-    out["dm"] = gather_shards_to_root(dm.to(torch.float32), shards, group) if matrix == "root" else None
+    send = [mean.reshape(-1, 1).to(torch.float64)]   # everything that goes to rank 0 travels in one NCCL group call
+    if matrix == "root":
+        send.append(dm.to(torch.float32))
     if want_emb:
-        out["emb"] = gather_shards_to_root(emb, shards, group)
+        send.append(emb)
+    got = gather_shards_to_root(send, shards, group)
+    out["mean"], out["dm"], out["emb"] = None, None, None
+    if got is not None:
+        out["mean"] = got[0].reshape(-1)
+        if matrix == "root":
+            out["dm"] = got[1]
+        if want_emb:
+            out["emb"] = got[-1]
     return out
 
 

@@ -175,3 +175,62 @@ def test_narrow_band_conv0_channels_on_dc_offset_input(record):
     err = float(np.abs(emb - ref).max())
     record("narrow_band_conv0_dc_offset", emb_max_abs_err=err)
     assert err <= EMB_TOL
+
+
+# ------------------------------------------------------------- evaluation harness (train_triplet.py:203-474)
+def test_evaluation_harness_entry_points(state_dict, tmp_path, record):
+    """The reference's evaluation methods on a small synthetic database: same tables as computing them the
+    reference's way (scipy ``cdist`` / ``np.diag`` / pandas groupby) from the per-file embeddings."""
+    import wave
+
+    import pandas as pd
+    from scipy.spatial.distance import cdist
+    from nomad_b200.evaluation import Evaluation
+    from nomad_b200.nomad import Nomad
+    rng = np.random.default_rng(4)
+
+    def wav(path, seconds, scale):
+        pcm = (rng.standard_normal(int(16000 * seconds)) * scale).astype(np.int16)
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+
+    (tmp_path / "nmr").mkdir(); (tmp_path / "wav").mkdir()
+    for i in range(5):
+        wav(tmp_path / "nmr" / f"clean{i}.wav", 1.0 + 0.3 * i, 2000)
+    rows = []
+    for c, cond in enumerate(["c01", "c02", "c03", "c04", "c05"]):
+        for k in range(3):
+            deg, ref = f"deg_{cond}_{k}.wav", f"ref_{cond}_{k}.wav"
+            wav(tmp_path / "wav" / deg, 0.8 + 0.2 * k, 1500 + 900 * c)
+            wav(tmp_path / "wav" / ref, 0.8 + 0.2 * k, 2000)
+            rows.append({"db": "DB1" if c < 4 else "DB2", "filepath_deg": deg, "filepath_ref": ref, "condition": cond,
+                         "mos": 4.5 - 0.7 * c + 0.05 * k, "Degradation": "noise", "Condition": c})
+    db = pd.DataFrame(rows)
+    nomad = Nomad(state_dict=state_dict)
+    ev = Evaluation(nomad, {"non_match_dir": str(tmp_path / "nmr"), "test_root_wav": str(tmp_path / "wav"),
+                            "test_mono_wav": str(tmp_path / "wav"), "db": None, "conds": None})
+    emb = lambda names, root: nomad.embed_files(np.array([os.path.join(root, n) for n in names])).cpu().numpy().astype(np.float64)
+    nmr = emb(os.listdir(tmp_path / "nmr"), str(tmp_path / "nmr"))
+    res = ev.eval_audio_quality(db)
+    worst = 0.0
+    for name, sub in db.groupby("db"):
+        d = cdist(emb(sub["filepath_deg"], str(tmp_path / "wav")), nmr).mean(1)
+        exp = pd.DataFrame({"condition": sub["condition"].values, "Distance": d, "mos": sub["mos"].values}).groupby("condition").mean()
+        got, corr = res[name]
+        assert list(got.index) == list(exp.index)
+        worst = max(worst, float(np.abs(got["Distance"].to_numpy() - exp["Distance"].to_numpy()).max()))
+        np.testing.assert_allclose(got["mos"].to_numpy(), exp["mos"].to_numpy(), atol=1e-12)
+        assert "SRCC" in corr and "PCC" in corr
+    fr = ev.eval_full_reference(db)
+    for name, sub in db.groupby("db"):
+        dd = np.diag(cdist(emb(sub["filepath_deg"], str(tmp_path / "wav")), emb(sub["filepath_ref"], str(tmp_path / "wav"))))
+        exp = pd.DataFrame({"condition": sub["condition"].values, "Distance": dd}).groupby("condition").mean()
+        worst = max(worst, float(np.abs(fr[name][0]["Distance"].to_numpy() - exp["Distance"].to_numpy()).max()))
+    di = ev.eval_degradation_intensity(db)
+    assert list(di) == ["noise"] and len(di["noise"][0]) == 5 and -1.0 <= di["noise"][1] <= 1.0
+    lvl, order = ev.eval_degr_level(db["filepath_deg"], root=str(tmp_path / "wav"))
+    assert list(lvl["Distance"]) == sorted(lvl["Distance"]) and sorted(order) == ["c01 0", "c01 1", "c01 2", "c02 0", "c02 1",
+                                                                                 "c02 2", "c03 0", "c03 1", "c03 2", "c04 0",
+                                                                                 "c04 1", "c04 2", "c05 0", "c05 1", "c05 2"]
+    record("evaluation_harness", distance_max_abs_err_vs_scipy=worst)
+    assert worst <= 1e-5
