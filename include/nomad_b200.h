@@ -49,6 +49,14 @@ typedef struct {
     int64_t numel;
 } nomad_b200_tensor;
 
+/* Arithmetic class of the scoring path (``precision_mode``).  The reference is fp32 everywhere (nomad.py:226-230).
+ *   FP16: fp16 tensor-core operands, fp32 accumulation / residual stream / statistics: embeddings within 1e-3 of the
+ *         fp32 reference (measured ~3.5e-4) -- the throughput mode.
+ *   FP32: every tensor-core operand as hi + lo fp16 planes, three MMA passes per product (~22 significant bits), fp32
+ *         attention and libdevice erff GELU: embeddings within 1e-5 of the reference arithmetic. */
+#define NOMAD_B200_PRECISION_FP16 0
+#define NOMAD_B200_PRECISION_FP32 1
+
 /* GEMM back end selector (``gemm_impl``): the tensor-core kernel is the product; the SIMT kernel
  * exists so the GPU tests can cross-check it on device. */
 #define NOMAD_B200_GEMM_TCGEN05 0
@@ -59,7 +67,13 @@ NOMAD_B200_API const char* nomad_b200_version(void);
 
 /* Replaces model construction + ``load_state_dict`` (nomad.py:53-68).  Folds weight-norm, permutes
  * conv weights to K-major, fuses q/k/v, converts to op_t and uploads to ``device``. */
-NOMAD_B200_API int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors, int device);
+NOMAD_B200_API int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors,
+                                     int precision_mode, int device);
+/* Switch a handle created with NOMAD_B200_PRECISION_FP32 between the two arithmetic classes (a handle created with
+ * NOMAD_B200_PRECISION_FP16 holds the fp16 weights only).  The scoring entry points (embed, score, layers_fwd and
+ * their _host variants) honour the mode; the loss path always runs fp16 operands. */
+NOMAD_B200_API int nomad_b200_set_precision(nomad_b200_handle* h, int precision_mode);
+NOMAD_B200_API int nomad_b200_get_precision(nomad_b200_handle* h);
 NOMAD_B200_API int nomad_b200_destroy(nomad_b200_handle* h);
 NOMAD_B200_API int nomad_b200_set_gemm_impl(nomad_b200_handle* h, int gemm_impl);
 
@@ -75,6 +89,9 @@ NOMAD_B200_API int nomad_b200_set_loss_head(nomad_b200_handle* h, const float* w
  * conv, attention and pooling).  ``emb`` receives B x 256 unit-norm fp32 rows.
  * Fails if an utterance is shorter than NOMAD_B200_MIN_SAMPLES (the reference raises RuntimeError). */
 NOMAD_B200_API size_t nomad_b200_embed_workspace_bytes(const int64_t* sample_offsets, int B);
+/* The plain *_workspace_bytes functions size the workspace for NOMAD_B200_PRECISION_FP16; a handle in FP32 mode needs
+ * the size the *_mode variants report (hi + lo planes, fp32 QKV rows). */
+NOMAD_B200_API size_t nomad_b200_embed_workspace_bytes_mode(const int64_t* sample_offsets, int B, int precision_mode);
 NOMAD_B200_API int nomad_b200_embed(nomad_b200_handle* h, const float* wav_dev, const int64_t* sample_offsets, int B,
                      float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Same, HOST buffers in and out (pinned or pageable); H2D + compute + D2H + stream sync inside. */
@@ -93,6 +110,7 @@ NOMAD_B200_API int nomad_b200_loss_fwd_bwd(nomad_b200_handle* h, const float* es
 /* ``LossNetLayers.forward`` (nomad.py:243-258): the 12 layer outputs (12 x B x T x 768 fp32, layer
  * major) and the head output (B x 256) for a fixed-length batch.  Either output may be NULL. */
 NOMAD_B200_API size_t nomad_b200_layers_workspace_bytes(int B, int64_t N);
+NOMAD_B200_API size_t nomad_b200_layers_workspace_bytes_mode(int B, int64_t N, int precision_mode);
 NOMAD_B200_API int64_t nomad_b200_num_frames(int64_t n_samples);
 NOMAD_B200_API int nomad_b200_layers_fwd(nomad_b200_handle* h, const float* wav_dev, int B, int64_t N, float* layers_dev,
                           float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
@@ -115,6 +133,7 @@ NOMAD_B200_API int nomad_b200_cdist_mean_host(const float* deg_host, int64_t n, 
  * HOST memory (staged H2D overlapping the front end), writes its outputs to HOST memory (emb_host / dm_host may be
  * NULL) and synchronises the stream. */
 NOMAD_B200_API size_t nomad_b200_score_workspace_bytes(const int64_t* sample_offsets, int B, int64_t m);
+NOMAD_B200_API size_t nomad_b200_score_workspace_bytes_mode(const int64_t* sample_offsets, int B, int64_t m, int precision_mode);
 NOMAD_B200_API int nomad_b200_score(nomad_b200_handle* h, const float* wav_dev, const int64_t* sample_offsets, int B,
                      const float* nmr_dev, int64_t m, float* emb_dev, float* dm_dev, double* row_mean_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);

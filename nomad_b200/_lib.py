@@ -24,11 +24,16 @@ class Tensor(C.Structure):
 PROTOTYPES = {
     "nomad_b200_last_error": (C.c_char_p, []),
     "nomad_b200_version": (C.c_char_p, []),
-    "nomad_b200_create": (C.c_int, [C.POINTER(c_vp), C.POINTER(Tensor), C.c_int, C.c_int]),
+    "nomad_b200_create": (C.c_int, [C.POINTER(c_vp), C.POINTER(Tensor), C.c_int, C.c_int, C.c_int]),
+    "nomad_b200_set_precision": (C.c_int, [c_vp, C.c_int]),
+    "nomad_b200_get_precision": (C.c_int, [c_vp]),
     "nomad_b200_destroy": (C.c_int, [c_vp]),
     "nomad_b200_set_gemm_impl": (C.c_int, [c_vp, C.c_int]),
     "nomad_b200_set_loss_head": (C.c_int, [c_vp, c_vp, c_vp]),
     "nomad_b200_embed_workspace_bytes": (C.c_size_t, [C.POINTER(c_i64), C.c_int]),
+    "nomad_b200_embed_workspace_bytes_mode": (C.c_size_t, [C.POINTER(c_i64), C.c_int, C.c_int]),
+    "nomad_b200_layers_workspace_bytes_mode": (C.c_size_t, [C.c_int, c_i64, C.c_int]),
+    "nomad_b200_score_workspace_bytes_mode": (C.c_size_t, [C.POINTER(c_i64), C.c_int, c_i64, C.c_int]),
     "nomad_b200_embed": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_vp, C.c_size_t, c_vp]),
     "nomad_b200_embed_host": (C.c_int, [c_vp, c_vp, C.POINTER(c_i64), C.c_int, c_vp, c_vp, C.c_size_t, c_vp]),
     "nomad_b200_loss_workspace_bytes": (C.c_size_t, [C.c_int, c_i64, C.c_int]),

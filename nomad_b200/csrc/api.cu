@@ -379,6 +379,79 @@ static int build_weights(Handle* h, TensorTable& tt) {
     return 0;
 }
 
+// fp32-class mode: every GEMM weight as hi + lo planes of w * 2^k (see precise.cu)
+static int upload_split(Handle* h, const std::vector<float>& w, SplitW* out) {
+    float mx = 0.f;
+    for (float v : w) mx = std::fmax(mx, std::fabs(v));
+    int k = 0;
+    if (mx > 0.f) k = (int)std::floor(std::log2(16000.0f / mx));
+    k = k < -24 ? -24 : (k > 24 ? 24 : k);
+    const float sc = std::ldexp(1.0f, k);
+    std::vector<op_t> hi(w.size()), lo(w.size());
+    for (size_t i = 0; i < w.size(); ++i) {
+        const float v = w[i] * sc;
+        hi[i] = f2op(v);
+        lo[i] = f2op(v - op2f(hi[i]));
+    }
+    NB_TRY(upload(h, hi, &out->hi));
+    NB_TRY(upload(h, lo, &out->lo));
+    out->inv_scale = std::ldexp(1.0f, -k);
+    return 0;
+}
+
+static int build_weights_precise(Handle* h, TensorTable& tt) {
+    PreciseWeights& pw = h->pw;
+    const std::string P = "ssl_model.";
+    for (int l = 1; l < 7; ++l) {
+        const int k = CONV_KERNEL[l];
+        GET(cw, P + "feature_extractor.conv_layers." + std::to_string(l) + ".0.weight", 512LL * 512 * k);
+        std::vector<float> fw((size_t)512 * 512 * k);  // (cout, cin, tap) -> [cout][tap * 512 + cin]
+        for (int o = 0; o < 512; ++o)
+            for (int c = 0; c < 512; ++c)
+                for (int j = 0; j < k; ++j) fw[(size_t)o * (k * 512) + (size_t)j * 512 + c] = cw[((size_t)o * 512 + c) * k + j];
+        NB_TRY(upload_split(h, fw, &pw.conv[l]));
+    }
+    GET(pwt, P + "post_extract_proj.weight", 768LL * 512);
+    NB_TRY(upload_split(h, std::vector<float>(pwt, pwt + 768 * 512), &pw.proj));
+    GET(pv, P + "encoder.pos_conv.0.weight_v", 768LL * POS_GC * POS_K);
+    GET(pg, P + "encoder.pos_conv.0.weight_g", POS_K);
+    {
+        std::vector<double> nrm(POS_K, 0.0);
+        for (size_t i = 0; i < (size_t)768 * POS_GC; ++i)
+            for (int k = 0; k < POS_K; ++k) nrm[k] += (double)pv[i * POS_K + k] * pv[i * POS_K + k];
+        for (int k = 0; k < POS_K; ++k) nrm[k] = (double)pg[k] / std::sqrt(nrm[k]);
+        std::vector<float> fw((size_t)POS_G * POS_GC * POS_K * POS_GC);  // [g][n][tap * 48 + c]
+        for (int g = 0; g < POS_G; ++g)
+            for (int n = 0; n < POS_GC; ++n)
+                for (int c = 0; c < POS_GC; ++c)
+                    for (int k = 0; k < POS_K; ++k)
+                        fw[((size_t)(g * POS_GC + n)) * (POS_K * POS_GC) + (size_t)k * POS_GC + c] =
+                            (float)((double)pv[((size_t)(g * POS_GC + n) * POS_GC + c) * POS_K + k] * nrm[k]);
+        NB_TRY(upload_split(h, fw, &pw.pos));
+    }
+    for (int l = 0; l < LAYERS; ++l) {
+        const std::string Q = P + "encoder.layers." + std::to_string(l) + ".";
+        GET(wq, Q + "self_attn.q_proj.weight", 768LL * 768);
+        GET(wk, Q + "self_attn.k_proj.weight", 768LL * 768);
+        GET(wv, Q + "self_attn.v_proj.weight", 768LL * 768);
+        std::vector<float> v((size_t)2304 * 768);
+        for (size_t i = 0; i < (size_t)768 * 768; ++i) {
+            v[i] = wq[i] * 0.125f;  // head_dim^-0.5, exact
+            v[(size_t)768 * 768 + i] = wk[i];
+            v[(size_t)2 * 768 * 768 + i] = wv[i];
+        }
+        NB_TRY(upload_split(h, v, &pw.qkv[l]));
+        GET(wo, Q + "self_attn.out_proj.weight", 768LL * 768);
+        GET(w1, Q + "fc1.weight", 3072LL * 768);
+        GET(w2, Q + "fc2.weight", 768LL * 3072);
+        NB_TRY(upload_split(h, std::vector<float>(wo, wo + 768 * 768), &pw.o[l]));
+        NB_TRY(upload_split(h, std::vector<float>(w1, w1 + (size_t)3072 * 768), &pw.fc1[l]));
+        NB_TRY(upload_split(h, std::vector<float>(w2, w2 + (size_t)768 * 3072), &pw.fc2[l]));
+    }
+    pw.built = true;
+    return 0;
+}
+
 // ================================================================================================
 // Forward pass
 static constexpr int META_SLOTS = 4;
@@ -613,8 +686,11 @@ using namespace nb;
 
 extern "C" {
 
-int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors, int device) {
+int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors, int n_tensors, int precision_mode,
+                      int device) {
     NB_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "create: bad arguments");
+    NB_CHECK(precision_mode == NOMAD_B200_PRECISION_FP16 || precision_mode == NOMAD_B200_PRECISION_FP32,
+             "create: precision_mode must be 0 (fp16 operands) or 1 (fp32-class split operands)");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     NB_CHECK(ce == cudaSuccess && ndev > 0,
@@ -631,13 +707,26 @@ int nomad_b200_create(nomad_b200_handle** out, const nomad_b200_tensor* tensors,
     TensorTable tt;
     for (int i = 0; i < n_tensors; ++i)
         if (tensors[i].name && tensors[i].data) tt.map[tensors[i].name] = &tensors[i];
-    if (build_weights(&hh->h, tt)) {
+    if (build_weights(&hh->h, tt) || (precision_mode == NOMAD_B200_PRECISION_FP32 && build_weights_precise(&hh->h, tt))) {
         nomad_b200_destroy(hh);
         return 1;
     }
+    hh->h.precision = precision_mode;
     *out = hh;
     return 0;
 }
+
+int nomad_b200_set_precision(nomad_b200_handle* hh, int precision_mode) {
+    NB_TRY(check_handle(hh));
+    NB_CHECK(precision_mode == NOMAD_B200_PRECISION_FP16 || precision_mode == NOMAD_B200_PRECISION_FP32,
+             "precision_mode must be 0 (fp16 operands) or 1 (fp32-class split operands)");
+    NB_CHECK(precision_mode == NOMAD_B200_PRECISION_FP16 || hh->h.pw.built,
+             "this handle was created with precision_mode 0: the fp32-class weights were not built");
+    hh->h.precision = precision_mode;
+    return 0;
+}
+
+int nomad_b200_get_precision(nomad_b200_handle* hh) { return hh ? hh->h.precision : -1; }
 
 int nomad_b200_destroy(nomad_b200_handle* hh) {
     if (!hh) return 0;
@@ -695,6 +784,15 @@ size_t nomad_b200_embed_workspace_bytes(const int64_t* sample_offsets, int B) {
     return carve_workspace(p, nullptr, nullptr, false);
 }
 
+size_t nomad_b200_embed_workspace_bytes_mode(const int64_t* sample_offsets, int B, int precision_mode) {
+    Plan p;
+    if (make_plan(sample_offsets, B, &p)) return 0;
+    const size_t a = carve_workspace(p, nullptr, nullptr, false);
+    if (precision_mode != NOMAD_B200_PRECISION_FP32) return a;
+    const size_t b = precise_workspace_bytes(p);
+    return a > b ? a : b;
+}
+
 }  // extern "C"
 
 // `pipe`: the caller stages the waveform in groups on a side stream (see FrontPipe); `issue_copies` is called right
@@ -710,11 +808,17 @@ static int embed_impl(nomad_b200_handle* hh, const float* wav_dev, const int64_t
     NB_TRY(make_plan(sample_offsets, B, &p));
     // wav_dev points at sample sample_offsets[0]
     for (auto& m : p.utt) m.wav_off -= sample_offsets[0];
+    NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "embed: workspace must be 1024-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->precision == NOMAD_B200_PRECISION_FP32) {  // fp32-class mode (precise.cu); host copies are waited for up front
+        NB_TRY(issue_copies());
+        if (pipe != nullptr)
+            for (int g = 0; g < pipe->n_groups; ++g) NB_CUDA(cudaStreamWaitEvent(st, pipe->copied[g], 0));
+        return embed_precise(h, p, workspace_dev, workspace_bytes, wav_dev, st, nullptr, 0, h->w.head_wt, h->w.head_b, emb_dev);
+    }
     Workspace ws;
     const size_t need = carve_workspace(p, workspace_dev, &ws, false);
     NB_CHECK(workspace_bytes >= need, "embed: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "embed: workspace must be 1024-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     NB_TRY(upload_meta(h, p, ws, st));
     NB_TRY(issue_copies());
     NB_TRY(forward_encoder(h, p, ws, wav_dev, st, nullptr, 0, pipe));
@@ -782,9 +886,8 @@ int nomad_b200_embed_host(nomad_b200_handle* hh, const float* wav_host, const in
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = sample_offsets[B] - sample_offsets[0];
     // the tail of the caller's workspace holds the staged waveform and the embeddings
-    Plan p;
-    NB_TRY(make_plan(sample_offsets, B, &p));
-    const size_t core = carve_workspace(p, nullptr, nullptr, false);
+    const size_t core = align_up(nomad_b200_embed_workspace_bytes_mode(sample_offsets, B, hh->h.precision), 1024);
+    NB_CHECK(core != 0, "embed_host: %s", nomad_b200_last_error());
     const size_t wav_bytes = align_up((size_t)total * 4 + 64, 1024), emb_bytes = align_up((size_t)B * EMB * 4, 1024);
     NB_CHECK(workspace_bytes >= core + wav_bytes + emb_bytes,
              "embed_host: workspace too small (%zu < %zu bytes; embed_workspace_bytes + 4*samples + 1024*B + 4096)",
@@ -852,6 +955,12 @@ size_t nomad_b200_layers_workspace_bytes(int B, int64_t N) {
     return nomad_b200_embed_workspace_bytes(off.data(), B);
 }
 
+size_t nomad_b200_layers_workspace_bytes_mode(int B, int64_t N, int precision_mode) {
+    std::vector<int64_t> off;
+    if (uniform_offsets(B, N, &off)) return 0;
+    return nomad_b200_embed_workspace_bytes_mode(off.data(), B, precision_mode);
+}
+
 int nomad_b200_layers_fwd(nomad_b200_handle* hh, const float* wav_dev, int B, int64_t N, float* layers_dev,
                           float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     NB_TRY(check_handle(hh));
@@ -862,10 +971,15 @@ int nomad_b200_layers_fwd(nomad_b200_handle* hh, const float* wav_dev, int B, in
     NB_TRY(uniform_offsets(B, N, &off));
     Plan p;
     NB_TRY(make_plan(off.data(), B, &p));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->precision == NOMAD_B200_PRECISION_FP32) {
+        const bool lh = h->has_loss_head;
+        return embed_precise(h, p, workspace_dev, workspace_bytes, wav_dev, st, layers_dev, p.max_T,
+                             lh ? h->w.loss_head_wt : h->w.head_wt, lh ? h->w.loss_head_b : h->w.head_b, emb_dev);
+    }
     Workspace ws;
     const size_t need = carve_workspace(p, workspace_dev, &ws, false);
     NB_CHECK(workspace_bytes >= need, "layers_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    cudaStream_t st = (cudaStream_t)stream;
     NB_TRY(upload_meta(h, p, ws, st));
     NB_TRY(forward_encoder(h, p, ws, wav_dev, st, layers_dev, p.max_T));
     if (emb_dev) {
@@ -901,7 +1015,11 @@ int nomad_b200_cdist_mean(const float* deg_dev, int64_t n, const float* nmr_dev,
 
 // ---- one batch of Nomad.predict: embed + distance rows against a resident NMR set ---------------------------------
 size_t nomad_b200_score_workspace_bytes(const int64_t* sample_offsets, int B, int64_t m) {
-    const size_t e = nomad_b200_embed_workspace_bytes(sample_offsets, B);
+    return nomad_b200_score_workspace_bytes_mode(sample_offsets, B, m, NOMAD_B200_PRECISION_FP16);
+}
+
+size_t nomad_b200_score_workspace_bytes_mode(const int64_t* sample_offsets, int B, int64_t m, int precision_mode) {
+    const size_t e = nomad_b200_embed_workspace_bytes_mode(sample_offsets, B, precision_mode);
     if (e == 0 || m < 0) return 0;
     const long long total = sample_offsets[B] - sample_offsets[0];
     // embed workspace | cdist workspace | staged waveform, embeddings, matrix rows, means (the *_host variant)
@@ -912,8 +1030,9 @@ size_t nomad_b200_score_workspace_bytes(const int64_t* sample_offsets, int B, in
 int nomad_b200_score(nomad_b200_handle* hh, const float* wav_dev, const int64_t* sample_offsets, int B,
                      const float* nmr_dev, int64_t m, float* emb_dev, float* dm_dev, double* row_mean_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_TRY(check_handle(hh));
     NB_CHECK(sample_offsets && B > 0 && m >= 0 && emb_dev && row_mean_dev, "score: bad arguments");
-    const size_t e = align_up(nomad_b200_embed_workspace_bytes(sample_offsets, B), 1024);
+    const size_t e = align_up(nomad_b200_embed_workspace_bytes_mode(sample_offsets, B, hh->h.precision), 1024);
     NB_CHECK(e != 0, "score: %s", nomad_b200_last_error());
     const size_t c = nomad_b200_cdist_workspace_bytes(B, m);
     NB_CHECK(workspace_dev && workspace_bytes >= e + c, "score: workspace too small (%zu < %zu bytes)", workspace_bytes, e + c);
@@ -926,11 +1045,11 @@ int nomad_b200_score_host(nomad_b200_handle* hh, const float* wav_host, const in
                           void* workspace_dev, size_t workspace_bytes, void* stream) {
     NB_TRY(check_handle(hh));
     NB_CHECK(wav_host && sample_offsets && B > 0 && m >= 0 && row_mean_host, "score_host: bad arguments");
-    const size_t need = nomad_b200_score_workspace_bytes(sample_offsets, B, m);
+    const size_t need = nomad_b200_score_workspace_bytes_mode(sample_offsets, B, m, hh->h.precision);
     NB_CHECK(need != 0, "score_host: %s", nomad_b200_last_error());
     NB_CHECK(workspace_dev && workspace_bytes >= need, "score_host: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     const long long total = sample_offsets[B] - sample_offsets[0];
-    const size_t e = align_up(nomad_b200_embed_workspace_bytes(sample_offsets, B), 1024);
+    const size_t e = align_up(nomad_b200_embed_workspace_bytes_mode(sample_offsets, B, hh->h.precision), 1024);
     const size_t c = align_up(nomad_b200_cdist_workspace_bytes(B, m), 1024);
     char* base = (char*)workspace_dev;
     float* wav_dev = (float*)(base + e + c);

@@ -127,13 +127,18 @@ __device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& e, fl
 }
 
 // FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
-template <bool FULL, int EF>
+template <bool FULL, int EF, bool PREC = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
     const int flags = epi_flags<EF>(e);
     const long long off = row * e.ldo + col0 + (long long)b * e.out_bstride;
     const long long woff = (row - lane) * e.ldo + col0 + (long long)b * e.out_bstride;  // this warp's first row
+    if (PREC) {
+        const float sc = e.acc_scale;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
+    }
     if ((FULL || row_ok) && (flags & EPI_BIAS)) {
         const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bstride + col0);
 #pragma unroll
@@ -171,7 +176,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
     } else if (flags & EPI_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_act(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = PREC ? gelu_erf_exact(v[j]) : gelu_act(v[j]);
     }
     if ((FULL || row_ok) && (flags & EPI_MUL_AUX)) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
@@ -253,6 +258,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
     if (flags & EPI_OUT_H16) {
         stage_put_h16(reinterpret_cast<op_t*>(stage), v, lane);
         stage_flush_h16(reinterpret_cast<op_t*>(stage), e.out_h + woff, e.ldo, rows_valid, ncols, lane);
+        if (PREC) {  // lo plane: what the fp16 rounding of the hi plane left over
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] -= op2f(f2op(v[j]));
+            stage_put_h16(reinterpret_cast<op_t*>(stage), v, lane);
+            stage_flush_h16(reinterpret_cast<op_t*>(stage), e.out_l + woff, e.ldo, rows_valid, ncols, lane);
+        }
     }
 }
 
@@ -372,7 +383,7 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The accumulator stage is handed back
 // to the MMA warp as soon as the last TMEM load has landed (before that chunk's math and stores).
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
-template <int CHUNKS, bool PAIR, bool CDIST, int EF>
+template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
@@ -420,8 +431,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
-            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
-            else epilogue_chunk<false, EF>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
+            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF, PREC>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
+            else epilogue_chunk<false, EF, PREC>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     rhave = rc.rhave;
@@ -430,9 +441,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool CDIST>
+// PREC: operands are hi + lo planes (tmA / tmB = hi, tmA2 / tmB2 = lo) and the K loop runs three segments,
+// A_hi B_hi, A_lo B_hi, A_hi B_lo, into the same accumulator (see EPI_PRECISE).
+template <int BN, bool CDIST, bool PREC = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmArgs args) {
     using Cfg = TileCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -448,6 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.m_tiles * args.n_tiles * args.batch;
     const int k_blocks = (args.K + BK - 1) / BK;
+    const int k_total = PREC ? 3 * k_blocks : k_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -483,18 +498,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n_blk = tile % args.n_tiles;
                 const int m_blk = (tile / args.n_tiles) % args.m_tiles;
                 const int b = tile / (args.n_tiles * args.m_tiles);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kq = 0; kq < k_total; ++kq) {
+                    const int seg = PREC ? kq / k_blocks : 0, kb = PREC ? kq - seg * k_blocks : kq;
+                    const CUtensorMap* mA = (PREC && seg == 1) ? &tmA2 : &tmA;
+                    const CUtensorMap* mB = (PREC && seg == 2) ? &tmB2 : &tmB;
                     mbar_wait_role(&empty_bar[stage], phase ^ 1, args.sleep_ns);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     if (args.a_wrap > 0) {
                         const int kk = kb * BK;
-                        tma_load_3d(sa, &tmA, &full_bar[stage], kk % args.a_wrap, m_blk * BM + kk / args.a_wrap, b);
+                        tma_load_3d(sa, mA, &full_bar[stage], kk % args.a_wrap, m_blk * BM + kk / args.a_wrap, b);
                     } else {
-                        tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, b);
+                        tma_load_3d(sa, mA, &full_bar[stage], kb * BK, m_blk * BM, b);
                     }
-                    tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN, b);
+                    tma_load_3d(sb, mB, &full_bar[stage], kb * BK, n_blk * BN, b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -512,7 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait_role(&tmem_empty[as], aphase ^ 1, args.sleep_ns);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = 0; kb < k_total; ++kb) {
                     mbar_wait_role(&full_bar[stage], phase, args.sleep_ns);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -525,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+                    if (kb == k_total - 1) umma_commit(&tmem_full[as]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -549,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats<-1>(args, row);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<CHUNKS, false, CDIST, -1>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
+            epilogue_tile<CHUNKS, false, CDIST, -1, PREC>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
                                          row_st, nullptr, no_prefetch, nullptr, nullptr, 0, n_blk * 2 + h);
         }
@@ -590,9 +608,10 @@ struct Pair256 {
     }
 };
 
-template <int NEW, bool CDIST, bool RPF, int EF>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
+template <int NEW, bool CDIST, bool RPF, int EF, bool PREC = false>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmArgs args) {
     using Cfg = Pair256;
     constexpr int STAGES = Cfg::stages(NEW, RPF);
     constexpr int BN = Cfg::BN;
@@ -615,6 +634,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_tiles = args.m_tiles * args.n_tiles * args.batch;  // m_tiles counts 256-row tiles here
     const int k_blocks = (args.K + BK - 1) / BK;
+    const int k_total = PREC ? 3 * k_blocks : k_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -650,18 +670,21 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int b = tile / (args.n_tiles * args.m_tiles);
                 const int row0 = m_blk * 256 + (int)rank * BM;
                 const int col0 = n_blk * BN + (int)rank * (BN / 2);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kq = 0; kq < k_total; ++kq) {
+                    const int seg = PREC ? kq / k_blocks : 0, kb = PREC ? kq - seg * k_blocks : kq;
+                    const CUtensorMap* mA = (PREC && seg == 1) ? &tmA2 : &tmA;
+                    const CUtensorMap* mB = (PREC && seg == 2) ? &tmB2 : &tmB;
                     mbar_wait_role(&empty_bar[stage], phase ^ 1, args.sleep_ns);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                     if (args.a_wrap > 0) {
                         const int kk = kb * BK;
-                        tma_load_3d_pair(sa, &tmA, &full_bar[stage], kk % args.a_wrap, row0 + kk / args.a_wrap, b);
+                        tma_load_3d_pair(sa, mA, &full_bar[stage], kk % args.a_wrap, row0 + kk / args.a_wrap, b);
                     } else {
-                        tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * BK, row0, b);
+                        tma_load_3d_pair(sa, mA, &full_bar[stage], kb * BK, row0, b);
                     }
-                    tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * BK, col0, b);
+                    tma_load_3d_pair(sb, mB, &full_bar[stage], kb * BK, col0, b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -678,7 +701,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait_role(&tmem_empty[as], aphase ^ 1, args.sleep_ns);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = 0; kb < k_total; ++kb) {
                     mbar_wait_role(&full_bar[stage], phase, args.sleep_ns);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -688,7 +711,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     umma_commit_pair(&empty_bar[stage]);
-                    if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[as]);
+                    if (kb == k_total - 1) umma_commit_pair(&tmem_full[as]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -746,7 +769,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<HALF / 32, true, CDIST, EF>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+            epilogue_tile<HALF / 32, true, CDIST, EF, PREC>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
                                            row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h);
         }
@@ -907,45 +930,62 @@ static int prof_end(cudaStream_t st) {
     return 0;
 }
 
-template <int BN, bool CDIST>
+static int lo_operand(const GemmOperand& op, GemmOperand* out) {
+    *out = op;
+    if (op.lo != nullptr) out->ptr = op.lo;
+    return 0;
+}
+
+template <int BN, bool CDIST, bool PREC = false>
 static int launch_tc_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = TileCfg<BN>;
     static bool attr_set[64] = {false};  // the attribute is per device
     if (bool* flag = device_once_flag(attr_set)) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CDIST, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         *flag = true;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmA2, tmB2;
     NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
     NB_TRY(make_operand_map(&tmB, B, args.K, args.batch, args.umma_n));
+    GemmOperand Al, Bl;
+    lo_operand(A, &Al);
+    lo_operand(B, &Bl);
+    NB_TRY(make_operand_map(&tmA2, Al, args.K, args.batch, BM));
+    NB_TRY(make_operand_map(&tmB2, Bl, args.K, args.batch, args.umma_n));
     args.m_tiles = (args.M + BM - 1) / BM;
     args.n_tiles = (args.N + BN - 1) / BN;
     const long long tiles = (long long)args.m_tiles * args.n_tiles * args.batch;
     int grid = device_sm_count();
     if (tiles < grid) grid = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_kernel<BN, CDIST><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, args);
+    gemm_tc_kernel<BN, CDIST, PREC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
 }
 template <int BN>
 static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    if (args.epi.flags & EPI_PRECISE) return launch_tc_impl<BN, false, true>(st, A, B, args);
     return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
 }
 
-template <int NEW, bool CDIST, bool RPF = false, int EF = -1>
+template <int NEW, bool CDIST, bool RPF = false, int EF = -1, bool PREC = false>
 static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
     constexpr int SMEM = Cfg::smem_bytes(NEW, RPF);
     static bool attr_set[64] = {false};  // the attribute is per device
     if (bool* flag = device_once_flag(attr_set)) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         *flag = true;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmA2, tmB2;
     NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
     NB_TRY(make_operand_map(&tmB, B, args.K, args.batch, Cfg::BN / 2));
+    GemmOperand Al, Bl;
+    lo_operand(A, &Al);
+    lo_operand(B, &Bl);
+    NB_TRY(make_operand_map(&tmA2, Al, args.K, args.batch, BM));
+    NB_TRY(make_operand_map(&tmB2, Bl, args.K, args.batch, Cfg::BN / 2));
     args.umma_n = Cfg::BN;
     args.m_tiles = (args.M + 255) / 256;
     args.n_tiles = (args.N + Cfg::BN - 1) / Cfg::BN;
@@ -953,12 +993,13 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, args);
+    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
 }
 static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
+    if (args.epi.flags & EPI_PRECISE) return launch_pair_impl<8, false, false, -1, true>(st, A, B, args);
     if (args.epi.flags & EPI_CDIST) return launch_pair_impl<16, true>(st, A, B, args);  // epilogue-bound (sqrt, sums, 4 B/pair out)
     // 16 epilogue warps hide the latency of a math-heavy (GELU) epilogue when the mainloop is short (FC1, K = 768:
     // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
@@ -1014,6 +1055,12 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
     static const unsigned sleep_ns = getenv("NOMAD_B200_GEMM_SLEEP") ? (unsigned)atoi(getenv("NOMAD_B200_GEMM_SLEEP")) : 0u;
     args.sleep_ns = sleep_ns;
     NB_CHECK(B.k_wrap == 0, "only the A operand may use wrapped K");
+    if (epi.flags & EPI_PRECISE) {
+        NB_CHECK(impl == 0 && A.lo != nullptr && B.lo != nullptr && epi.acc_scale > 0.f, "EPI_PRECISE needs hi + lo operand planes and a scale");
+        NB_CHECK(!(epi.flags & EPI_OUT_H16) || epi.out_l != nullptr, "EPI_PRECISE with a 16-bit output needs the lo plane pointer");
+        NB_CHECK(!(epi.flags & (EPI_CDIST | EPI_LN_FOLD | EPI_STATS_OUT | EPI_RESID_LN | EPI_SAVE_DGELU | EPI_MUL_AUX)),
+                 "EPI_PRECISE supports bias / GELU / residual / fp32 and split 16-bit outputs only");
+    }
     if (!(epi.flags & EPI_CDIST)) {
         NB_CHECK(N % 8 == 0 && epi.ldo % 8 == 0 && epi.out_bstride % 8 == 0,
                  "GEMM epilogue needs N, ldo, out_bstride multiples of 8 (N=%d ldo=%lld bstride=%lld)", N, epi.ldo,
@@ -1044,7 +1091,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
             const double used = (double)N / (((N + bn - 1) / bn) * (double)bn);
             return tile_eff * used * tiles / (std::ceil(tiles / sms) * sms);
         };
-        const bool use192 = (epi.flags & (EPI_STATS_OUT | EPI_CDIST)) ? false : (force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0));
+        const bool use192 = (epi.flags & (EPI_STATS_OUT | EPI_CDIST | EPI_PRECISE)) ? false : (force_bn ? force_bn == 192 : eff(192, 0.89) > eff(256, 1.0));
         if (use192) {
             args.umma_n = 192;
             return launch_tc<192>(st, A, B, args);

@@ -22,6 +22,12 @@ enum : int {
     // also emit per-row partial LayerNorm statistics of the fp32 output, one (mean, M2) pair per 64 columns, for
     // a later EPI_LN_FOLD / EPI_RESID_LN consumer (needs N % 256 == 0)
     EPI_STATS_OUT = 1024,
+    // fp32-class ("precise") mode, only in the PREC kernel instantiations: operands are hi + lo fp16 planes and the
+    // mainloop runs three K segments (A_hi B_hi + A_lo B_hi + A_hi B_lo, ~22 significant bits per product); the
+    // epilogue first multiplies the accumulator by acc_scale (weights are stored times a power of two so that their
+    // lo plane stays in fp16's normal range), uses libdevice erff for the GELU, and EPI_OUT_H16 stores the result as
+    // hi (out_h) + lo (out_l) planes.
+    EPI_PRECISE = 2048,
     EPI_SAVE_DGELU = 128,  // with EPI_GELU: also store gelu'(pre-activation) to aux_out (bf16/fp16), for the loss backward
 };
 
@@ -38,6 +44,7 @@ struct GemmOperand {
     // w > 0 ("wrapped K", the non-overlapping spelling of the same thing, needs w % 64 == 0):
     //   it lives at (r + k / w) * row_stride + k % w, with row_stride == w.
     int k_wrap;
+    const op_t* lo;  // EPI_PRECISE: the lo plane (same layout as ptr); nullptr otherwise
 };
 
 struct GemmEpilogue {
@@ -69,6 +76,8 @@ struct GemmEpilogue {
     const float* cd_a;        // [M][256] original fp32 rows (exact re-evaluation of near-zero distances)
     const float* cd_b;        // [N][256]
     float cd_inv_scale;       // acc * cd_inv_scale = dot product
+    float acc_scale;          // EPI_PRECISE: accumulator scale (2^-k of the weight tensor)
+    op_t* out_l;              // EPI_PRECISE + EPI_OUT_H16: lo plane of the output, same indexing as out_h
 };
 
 // C[b] = epilogue(A[b] (M x K) * B[b]^T (N x K)).  impl: 0 = tcgen05/TMA kernel, 1 = SIMT check kernel.

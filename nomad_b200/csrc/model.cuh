@@ -74,6 +74,20 @@ struct Weights {
     float* loss_head_b;
 };
 
+// fp32-class mode (precise.cu): a GEMM weight as hi + lo fp16 planes of w * 2^k (k per tensor, so that the lo plane
+// stays in fp16's normal range); inv_scale = 2^-k goes into the epilogue.
+struct SplitW {
+    op_t* hi;
+    op_t* lo;
+    float inv_scale;
+};
+struct PreciseWeights {
+    bool built = false;
+    SplitW conv[7]{};   // l = 1..6, same layout as Weights::conv_w
+    SplitW proj{}, pos{};
+    SplitW qkv[LAYERS]{}, o[LAYERS]{}, fc1[LAYERS]{}, fc2[LAYERS]{};
+};
+
 struct Plan {
     int B = 0;
     std::vector<UttMeta> utt;
@@ -126,7 +140,9 @@ struct Workspace {
 struct Handle {
     int device = 0;
     int gemm_impl = 0;
+    int precision = 0;          // 0: fp16 tensor-core operands (default), 1: fp32-class split operands (precise.cu)
     Weights w{};
+    PreciseWeights pw{};
     std::vector<void*> allocs;  // everything cudaMalloc'ed for the weights
     bool has_loss_head = false;
     char* meta_host = nullptr;  // pinned staging for the per-call metadata (UttMeta[B] + attention work list)
@@ -152,6 +168,10 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
 int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st);
 void build_attention_items(const Plan& p, std::vector<uint32_t>* items);
 GemmEpilogue epi_linear(int flags, const float* bias, const float* resid, float* out_f, op_t* out_h, long long ld);
+// precise.cu
+size_t precise_workspace_bytes(const Plan& p);
+int embed_precise(Handle* h, const Plan& p, void* workspace, size_t workspace_bytes, const float* wav, cudaStream_t st,
+                  float* layers_out, int layer_T, const float* head_wt, const float* head_b, float* emb_dev);
 
 }  // namespace nb
 

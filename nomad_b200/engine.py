@@ -15,6 +15,7 @@ from . import _lib
 from .weights import EMB_DIM, NUM_LAYERS, SSL_OUT_DIM
 
 MIN_SAMPLES = 400
+PRECISIONS = {"fp16": 0, "fp32": 1}   # NOMAD_B200_PRECISION_FP16 / _FP32
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -28,8 +29,14 @@ def _stream_ptr():
 class Engine:
     """One NOMAD model resident on one GPU."""
 
-    def __init__(self, state_dict, device: Optional[int] = None):
+    def __init__(self, state_dict, device: Optional[int] = None, precision: str = "fp16"):
+        """``precision``: "fp16" (fp16 tensor-core operands, embeddings within 1e-3 of the fp32 reference) or "fp32"
+        (split hi + lo operands, within 1e-5; ~3x the time).  An "fp32" engine holds both weight sets and can be
+        switched with :meth:`set_precision`."""
         self.lib = _lib.load()
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise _lib.NomadB200Error("nomad_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device_index = torch.cuda.current_device() if device is None else int(device)
@@ -47,7 +54,8 @@ class Engine:
             tens[i].numel = a.size
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.nomad_b200_create(C.byref(h), tens, len(names), self.device_index), "nomad_b200_create")
+            _lib.check(self.lib.nomad_b200_create(C.byref(h), tens, len(names), PRECISIONS[precision], self.device_index),
+                       "nomad_b200_create")
         self.handle = h
         self._ws: Optional[torch.Tensor] = None
         self._pinned: Optional[torch.Tensor] = None
@@ -67,6 +75,14 @@ class Engine:
     # ------------------------------------------------------------------ helpers
     def set_gemm_impl(self, impl: int):
         _lib.check(self.lib.nomad_b200_set_gemm_impl(self.handle, int(impl)), "set_gemm_impl")
+
+    def set_precision(self, precision: str):
+        _lib.check(self.lib.nomad_b200_set_precision(self.handle, PRECISIONS[precision]), "set_precision")
+        self.precision = precision
+
+    @property
+    def _mode(self) -> int:
+        return PRECISIONS[self.precision]
 
     def set_loss_head(self, weight: torch.Tensor, bias: torch.Tensor):
         w = np.ascontiguousarray(weight.detach().to(torch.float32).cpu().numpy())
@@ -101,7 +117,7 @@ class Engine:
         B = len(offsets) - 1
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
-        need = self.lib.nomad_b200_embed_workspace_bytes(off_p, B)
+        need = self.lib.nomad_b200_embed_workspace_bytes_mode(off_p, B, self._mode)
         if need == 0:
             raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
         ws = self.workspace(need)
@@ -125,7 +141,7 @@ class Engine:
         B = len(offsets) - 1
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
-        need = self.lib.nomad_b200_embed_workspace_bytes(off_p, B)
+        need = self.lib.nomad_b200_embed_workspace_bytes_mode(off_p, B, self._mode)
         if need == 0:
             raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
         total = int(offsets[-1] - offsets[0])
@@ -147,7 +163,7 @@ class Engine:
         B, m = len(offsets) - 1, nmr.shape[0]
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
-        need = self.lib.nomad_b200_score_workspace_bytes(off_p, B, m)
+        need = self.lib.nomad_b200_score_workspace_bytes_mode(off_p, B, m, self._mode)
         if need == 0:
             raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
         wp, wbytes = self._aligned(self.workspace(need))
@@ -167,7 +183,7 @@ class Engine:
         B, m = len(offsets) - 1, nmr.shape[0]
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         off_p = offsets.ctypes.data_as(C.POINTER(C.c_int64))
-        need = self.lib.nomad_b200_score_workspace_bytes(off_p, B, m)
+        need = self.lib.nomad_b200_score_workspace_bytes_mode(off_p, B, m, self._mode)
         if need == 0:
             raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
         wp, wbytes = self._aligned(self.workspace(need))
@@ -205,7 +221,7 @@ class Engine:
         wav = wav.to(self.device, torch.float32).contiguous()
         B, N = wav.shape
         T = self.num_frames(N)
-        need = self.lib.nomad_b200_layers_workspace_bytes(B, N)
+        need = self.lib.nomad_b200_layers_workspace_bytes_mode(B, N, self._mode)
         if need == 0:
             raise _lib.NomadB200Error(self.lib.nomad_b200_last_error().decode())
         ws = self.workspace(need)

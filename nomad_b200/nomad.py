@@ -146,7 +146,8 @@ class _NomadLossFn(torch.autograd.Function):
 
 class Nomad():
     def __init__(self, device=None, checkpoint: Optional[str] = None, seed: int = 1234,
-                 feature_grad_mult: float = 0.1, max_batch_seconds: float = 2000.0, state_dict=None):
+                 feature_grad_mult: float = 0.1, max_batch_seconds: float = 2000.0, state_dict=None,
+                 precision: Optional[str] = None):
         # *** DEVICE SETTINGS *** (nomad.py:38-49)
         if torch.cuda.is_available():
             self.DEVICE = 'cuda'
@@ -166,7 +167,10 @@ class Nomad():
             state_dict, self.weights_source = load_state_dict(checkpoint, seed)
         else:
             self.weights_source = "state_dict"
-        self.engine = Engine(state_dict, index)
+        # arithmetic class of the scoring path: "fp16" (tensor-core operands in fp16, scores within 1e-3 of the
+        # reference's fp32 arithmetic) or "fp32" (split operands, within 1e-5); the loss path always runs "fp16"
+        self.precision = precision or os.environ.get("NOMAD_B200_PRECISION", "fp16")
+        self.engine = Engine(state_dict, index, self.precision)
         self.model = TripletModel(self.engine)
         # NOMAD loss model shares the same network (nomad.py:70-72)
         self.lossnet_layers = LossNetLayers(self.engine)

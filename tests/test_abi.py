@@ -70,7 +70,7 @@ def test_compute_fails_loudly_without_gpu(lib):
     t = (_lib.Tensor * 1)()
     t[0].name, t[0].data, t[0].numel = name, arr.ctypes.data_as(C.c_void_p), arr.size
     h = C.c_void_p()
-    assert lib.nomad_b200_create(C.byref(h), t, 1, 0) != 0
+    assert lib.nomad_b200_create(C.byref(h), t, 1, 0, 0) != 0
     assert b"no CPU fallback" in lib.nomad_b200_last_error()
     from nomad_b200.engine import Engine
     with pytest.raises(_lib.NomadB200Error):
