@@ -164,6 +164,13 @@ NOMAD_B200_API int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_
                          const float* bias, const float* resid, float* c_f32, void* c_f16, int64_t ldc, int flags,
                          int gemm_impl, void* stream);
 
+/* Same building block in fp32-class mode (NOMAD_B200_PRECISION_FP32): A and B as hi + lo fp16 planes, three K segments
+ * (A_hi B_hi + A_lo B_hi + A_hi B_lo) into one accumulator, times acc_scale, then flags 1 bias, 2 GELU (libdevice erff),
+ * 8 store fp32 (c_f32), 16 store hi + lo planes (c_hi, c_lo).  A: m x k (row stride lda), B: n x k, C: m x n (ldc). */
+NOMAD_B200_API int nomad_b200_gemm_split(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                          int m, int n, int k, float acc_scale, const float* bias, float* c_f32, void* c_hi, void* c_lo,
+                          int64_t ldc, int flags, void* stream);
+
 /* ---- ingest: ``Nomad.load_processing`` (nomad.py:192-212) after the file has been decoded to PCM ------------
  * pcm: n_frames x channels interleaved int16 DEVICE samples at ``sr`` Hz.  out: mono fp32 at ``target_sr``:
  * sample / 32768, mean of the first two channels when channels > 1 (nomad.py:199-200), torchaudio's default

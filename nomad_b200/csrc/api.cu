@@ -481,7 +481,8 @@ int upload_meta(Handle* h, const Plan& p, const Workspace& ws, cudaStream_t st) 
     memcpy(stage, p.utt.data(), meta_bytes);
     memcpy(stage + align_up(meta_bytes, 64), p.attn_items.data(), item_bytes);
     NB_CUDA(cudaMemcpyAsync(ws.meta, stage, meta_bytes, cudaMemcpyHostToDevice, st));
-    NB_CUDA(cudaMemcpyAsync(ws.attn_items, stage + align_up(meta_bytes, 64), item_bytes, cudaMemcpyHostToDevice, st));
+    if (item_bytes)
+        NB_CUDA(cudaMemcpyAsync(ws.attn_items, stage + align_up(meta_bytes, 64), item_bytes, cudaMemcpyHostToDevice, st));
     NB_CUDA(cudaEventRecord(ev[slot], st));
     return 0;
 }

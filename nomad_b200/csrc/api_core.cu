@@ -60,4 +60,22 @@ int nomad_b200_gemm_f16(const void* a_f16, int64_t a_rows, int64_t lda, int k_wr
     return nb::gemm_h16((cudaStream_t)stream, A, B, m, n, k, batch, e, gemm_impl);
 }
 
+int nomad_b200_gemm_split(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int m, int n,
+                          int k, float acc_scale, const float* bias, float* c_f32, void* c_hi, void* c_lo, int64_t ldc,
+                          int flags, void* stream) {
+    nb::GemmOperand A{(const nb::op_t*)a_hi, m, lda, 0, 0, (const nb::op_t*)a_lo};
+    nb::GemmOperand B{(const nb::op_t*)b_hi, n, k, 0, 0, (const nb::op_t*)b_lo};
+    nb::GemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.flags = (flags & (nb::EPI_BIAS | nb::EPI_GELU | nb::EPI_OUT_F32 | nb::EPI_OUT_H16)) | nb::EPI_PRECISE;
+    e.bias = bias;
+    e.bias_bstride = n;
+    e.out_f = c_f32;
+    e.out_h = (nb::op_t*)c_hi;
+    e.out_l = (nb::op_t*)c_lo;
+    e.ldo = ldc;
+    e.acc_scale = acc_scale;
+    return nb::gemm_h16((cudaStream_t)stream, A, B, m, n, k, 1, e, 0);
+}
+
 }  // extern "C"

@@ -383,7 +383,9 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // Epilogue of one warp for one tile: CHUNKS x (32 lanes x 32 columns).  The accumulator stage is handed back
 // to the MMA warp as soon as the last TMEM load has landed (before that chunk's math and stores).
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
-template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false>
+// PREC (single-CTA kernel only): the tile's sum lives in FOUR TMEM accumulators PACC columns apart (see gemm_tc_kernel);
+// they are added here in IEEE fp32.
+template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false, int PACC = 0>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
@@ -406,6 +408,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
+        if (PREC && PACC > 0) {
+#pragma unroll 1
+            for (int a = 1; a < 4; ++a) {
+                uint32_t q[32];
+                tmem_ld_32x32(taddr + a * PACC + c * 32, q);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+            }
+        }
         if (c == CHUNKS - 1) {  // every TMEM read of this tile has landed: release the accumulator stage now
             tc_fence_before();
             __syncwarp();
@@ -479,8 +491,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         mbar_fence_init();
     }
+    // PREC: four accumulators per tile and no double buffering.  The tensor core truncates its fp32 accumulator at
+    // every instruction (measured: relative bias -2^-25 per k16 step, profiles/r02_precise_probe.log), so a K = 768
+    // split GEMM accumulated in one chain of 144 steps is 5-10x less accurate than IEEE fp32.  The hi x hi segment is
+    // therefore spread over three accumulators (k-block mod 3) and the two small cross terms go to a fourth, which
+    // cuts the longest chain 9x; the epilogue adds the four in IEEE fp32.
+    constexpr int TCOLS = PREC ? 4 * Cfg::ACC_STRIDE : Cfg::TMEM_COLS;
     if (warp == 2) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_slot, TCOLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -525,11 +543,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
+                const int as = PREC ? 0 : (it & 1);
+                const uint32_t aphase = PREC ? (it & 1) : ((it >> 1) & 1);
                 mbar_wait_role(&tmem_empty[as], aphase ^ 1, args.sleep_ns);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+                uint32_t started = 0;  // PREC: accumulators that already hold a partial sum
                 for (int kb = 0; kb < k_total; ++kb) {
                     mbar_wait_role(&full_bar[stage], phase, args.sleep_ns);
                     tc_fence_after();
@@ -537,10 +555,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sb = sa + Cfg::A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sb);
+                    const int acc = PREC ? (kb < k_blocks ? kb % 3 : 3) : as;
+                    const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                    const uint32_t cont = PREC ? ((started >> acc) & 1u) : (kb ? 1u : 0u);
+                    started |= 1u << acc;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing K by 16 op_t = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cont | k) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
                     if (kb == k_total - 1) umma_commit(&tmem_full[as]);
@@ -561,13 +583,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n_blk = tile % args.n_tiles;
             const int m_blk = (tile / args.n_tiles) % args.m_tiles;
             const int b = tile / (args.n_tiles * args.m_tiles);
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+            const int as = PREC ? 0 : (it & 1);
+            const uint32_t aphase = PREC ? (it & 1) : ((it >> 1) & 1);
             const long long row = (long long)m_blk * BM + q * 32 + lane;
             const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats<-1>(args, row);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<CHUNKS, false, CDIST, -1, PREC>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
+            epilogue_tile<CHUNKS, false, CDIST, -1, PREC, Cfg::ACC_STRIDE>(args, tmem_base + (uint32_t)(as * Cfg::ACC_STRIDE + h * HALF) + ((uint32_t)(q * 32) << 16),
                                          row, n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
                                          row_st, nullptr, no_prefetch, nullptr, nullptr, 0, n_blk * 2 + h);
         }
@@ -576,7 +598,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, TCOLS);
     }
 }
 
@@ -965,7 +987,9 @@ static int launch_tc_impl(cudaStream_t st, const GemmOperand& A, const GemmOpera
 }
 template <int BN>
 static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
-    if (args.epi.flags & EPI_PRECISE) return launch_tc_impl<BN, false, true>(st, A, B, args);
+    if constexpr (BN <= 128) {
+        if (args.epi.flags & EPI_PRECISE) return launch_tc_impl<BN, false, true>(st, A, B, args);
+    }
     return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
 }
 
@@ -999,7 +1023,6 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     return 0;
 }
 static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
-    if (args.epi.flags & EPI_PRECISE) return launch_pair_impl<8, false, false, -1, true>(st, A, B, args);
     if (args.epi.flags & EPI_CDIST) return launch_pair_impl<16, true>(st, A, B, args);  // epilogue-bound (sqrt, sums, 4 B/pair out)
     // 16 epilogue warps hide the latency of a math-heavy (GELU) epilogue when the mainloop is short (FC1, K = 768:
     // 887 vs 841 TFLOP/s); with a long mainloop (conv, K = 1536) the extra warps only cost registers (1075 vs 1107).
@@ -1080,6 +1103,15 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
         return 0;
     }
     // CTA pairs (cta_group::2) for the big GEMMs; NOMAD_B200_PAIR=0 falls back to the single-CTA kernel
+    if (epi.flags & EPI_PRECISE) {  // four TMEM accumulators per tile: 128-wide (or 64-wide) single-CTA tiles
+        NB_CHECK(K >= 3 * BK, "EPI_PRECISE needs K >= %d", 3 * BK);
+        if (N > 64) {
+            args.umma_n = 128;
+            return launch_tc<128>(st, A, B, args);
+        }
+        args.umma_n = (N + 15) / 16 * 16;
+        return launch_tc<64>(st, A, B, args);
+    }
     if (use_pair_kernel(M, N, batch)) return launch_pair(st, A, B, args);
     if (N > 128) {
         // 256-wide tiles unless 192-wide ones waste enough fewer CTA-waves to pay for their lower per-tile

@@ -436,6 +436,7 @@ static GemmEpilogue epi_precise(int flags, const SplitW& w, const float* bias, c
 int embed_precise(Handle* h, const Plan& p, void* workspace, size_t workspace_bytes, const float* wav, cudaStream_t st,
                   float* layers_out, int layer_T, const float* head_wt, const float* head_b, float* emb_dev) {
     NB_CHECK(h->pw.built, "this handle was created without the fp32-class weights (precision_mode 1)");
+    NB_CHECK(p.B <= 65535, "embed (fp32 mode): at most 65535 utterances per call (got %d); split the batch", p.B);
     PWorkspace ws;
     const size_t need = carve_precise(p, workspace, &ws);
     NB_CHECK(workspace_bytes >= need, "embed (fp32 mode): workspace too small (%zu < %zu bytes)", workspace_bytes, need);

@@ -265,7 +265,7 @@ def test_fp32_mode_embeddings_within_1e5_of_fp64_oracle(engine32, state_dict, go
     layers, emb_b = engine32.layers(wav)
     l_err = float(np.abs(layers.cpu().numpy() - g["layers_b"]).max())
     record("fp32_mode_layers", layer_max_abs_err=l_err, layer_abs_max=float(np.abs(g["layers_b"]).max()))
-    assert l_err <= 1e-4   # |x| up to 4.6: relative 2e-5; the reference's own fp32 layers are ~1e-5 from fp64
+    assert l_err <= 5e-5   # |x| up to 4.6 (achieved ~1.4e-5; torch fp32 itself is ~4e-6 from fp64)
     # ragged long / short batch incl. tile-edge lengths
     gen = torch.Generator().manual_seed(3)
     lens = [16000, 163360, 20479, 20480, 20481, 400]
@@ -306,3 +306,32 @@ def test_fp16_handle_refuses_fp32_mode(engine):
     from nomad_b200._lib import NomadB200Error
     with pytest.raises(NomadB200Error, match="precision_mode 0"):
         engine.set_precision("fp32")
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 512), (1000, 2304, 768), (515, 768, 3072), (700, 48, 6144), (129, 512, 1536)])
+def test_split_operand_gemm_against_fp64(M, N, K, record):
+    """The fp32-class GEMM building block (hi + lo planes, 3 K segments, 4 TMEM accumulators) through the C ABI:
+    fp32 output within 3e-6 relative of the fp64 product of the original fp32 operands (cuBLAS fp32 class), hi + lo
+    output planes reconstructing it, bias + erff GELU epilogue."""
+    from nomad_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.04).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    sc = 2.0 ** np.floor(np.log2(16000.0 / float(w.abs().max())))
+    sp = lambda x: (x.half(), (x - x.half().float()).half())
+    (ah, al), (bh, bl) = sp(a), sp(w * sc)
+    c = torch.full((M, N), float("nan"), device="cuda")
+    ch = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    cl = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.nomad_b200_gemm_split(ah.data_ptr(), al.data_ptr(), K, bh.data_ptr(), bl.data_ptr(), M, N, K, float(1.0 / sc),
+                                         bias.data_ptr(), c.data_ptr(), ch.data_ptr(), cl.data_ptr(), N, 1 | 2 | 8 | 16, st), "split")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(a.double() @ w.double().T + bias.double())
+    scale = float((a.double() @ w.double().T).abs().max())
+    e1 = float((c.double() - ref).abs().max()) / scale
+    e2 = float((ch.double() + cl.double() - ref).abs().max()) / scale
+    record("split_operand_gemm", M=M, N=N, K=K, rel_err_f32_out=e1, rel_err_split_out=e2)
+    assert e1 <= 3e-6 and e2 <= 3e-6
