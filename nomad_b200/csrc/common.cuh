@@ -304,6 +304,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// TMA store of one box from shared memory (layout = the tensor map's swizzle) to global memory; coordinates past the
+// tensor's extent are clipped by the hardware.  Issued by ONE lane after the warp's generic-proxy writes to the box
+// have been fenced into the async proxy; the box may be overwritten once bulk_wait_read has returned.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cluster of 2, tcgen05 cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

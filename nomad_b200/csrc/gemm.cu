@@ -71,7 +71,41 @@ struct RowCtx {
     const float* vec;
     int vec_stride;  // floats per staged vector (= columns per epilogue warp)
     int vec_col0;    // first column of the staged range
+    // TMA stores (pair kernel, TS instantiations): the staged tile leaves through cp.async.bulk.tensor instead of being
+    // read back and stored by the lanes -- one instruction per tile instead of 8 (fp32) / 4 (16-bit) LDS + STG pairs per
+    // lane, and ragged edges are clipped by the hardware.  The staging layouts (stage_put_*) ARE the 128-byte / 64-byte
+    // TMA swizzles.  `pending` = 2 KB slots of this warp's staging area that an issued store may still be reading.
+    const CUtensorMap* tm_f;   // fp32 output map (box 32 x 32, SWIZZLE_128B) or nullptr
+    const CUtensorMap* tm_h;   // 16-bit output map (box 32 x 32, SWIZZLE_64B) or nullptr
+    const CUtensorMap* tm_a;   // 16-bit aux_out map or nullptr
+    uint32_t pending;
+    int stage_bytes;           // 4096 or 6144 per warp
+    int flip;                  // alternates the 16-bit slot when the area has no room for fp32 + 16-bit side by side
 };
+// wait until the slots in `mask` are free again (warp-uniform), then mark them as about to be in flight
+__device__ __forceinline__ void ts_acquire(RowCtx& rc, uint32_t mask, int lane) {
+    if (rc.pending & mask) {
+        if (lane == 0) bulk_wait_read();
+        rc.pending = 0;
+    }
+    __syncwarp();
+    rc.pending |= mask;
+}
+__device__ __forceinline__ void ts_issue(const CUtensorMap* map, const void* src, int col, long long row, int lane) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map, src, col, (int)row);
+        bulk_commit();
+    }
+}
+// byte offset of the 16-bit slot for this store (fp32 owns [0, 4096))
+__device__ __forceinline__ int ts_h16_slot(RowCtx& rc, bool f32_too) {
+    if (rc.stage_bytes >= 6144) return 4096;
+    if (f32_too) return 0;  // shares the fp32 area (rare combination in the 16-warp variants): serialised by ts_acquire
+    rc.flip ^= 1;
+    return rc.flip * 2048;
+}
 // (mean, rstd) of a 768-wide row from its LN_PARTS partial (mean, M2) pairs of 64 columns each (Chan et al.)
 __device__ __forceinline__ float2 ln_row_stats(const float* part, long long row) {
     const float4* p = reinterpret_cast<const float4*>(part + row * (2 * LN_PARTS));
@@ -127,7 +161,7 @@ __device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& e, fl
 }
 
 // FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
-template <bool FULL, int EF, bool PREC = false>
+template <bool FULL, int EF, bool PREC = false, bool TS = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
@@ -172,8 +206,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
         float g[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf_with_grad(v[j], g[j]);
-        stage_put_h16(reinterpret_cast<op_t*>(stage), g, lane);
-        stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
+        if (TS && rc.tm_a != nullptr) {
+            const int slot = ts_h16_slot(rc, false);
+            ts_acquire(rc, 1u << (slot >> 11), lane);
+            op_t* sp = reinterpret_cast<op_t*>(reinterpret_cast<char*>(stage) + slot);
+            stage_put_h16(sp, g, lane);
+            ts_issue(rc.tm_a, sp, col0, row - lane, lane);
+        } else {
+            stage_put_h16(reinterpret_cast<op_t*>(stage), g, lane);
+            stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
+        }
     } else if (flags & EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = PREC ? gelu_erf_exact(v[j]) : gelu_act(v[j]);
@@ -251,11 +293,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
                 make_float2(0.5f * (rc.pm + mc), rc.pM2 + M2c + 16.0f * d * d);
         }
     }
-    if (flags & EPI_OUT_F32) {
+    if (TS && rc.tm_f != nullptr && (flags & EPI_OUT_F32)) {
+        ts_acquire(rc, 3u, lane);
+        stage_put_f32(stage, v, lane);
+        ts_issue(rc.tm_f, stage, col0, row - lane, lane);
+    } else if (flags & EPI_OUT_F32) {
         stage_put_f32(stage, v, lane);
         stage_flush_f32(stage, e.out_f + woff, e.ldo, rows_valid, ncols, lane);
     }
-    if (flags & EPI_OUT_H16) {
+    if (TS && rc.tm_h != nullptr && (flags & EPI_OUT_H16)) {
+        const int slot = ts_h16_slot(rc, (flags & EPI_OUT_F32) != 0);
+        ts_acquire(rc, 1u << (slot >> 11), lane);
+        op_t* sp = reinterpret_cast<op_t*>(reinterpret_cast<char*>(stage) + slot);
+        stage_put_h16(sp, v, lane);
+        ts_issue(rc.tm_h, sp, col0, row - lane, lane);
+    } else if (flags & EPI_OUT_H16) {
         stage_put_h16(reinterpret_cast<op_t*>(stage), v, lane);
         stage_flush_h16(reinterpret_cast<op_t*>(stage), e.out_h + woff, e.ldo, rows_valid, ncols, lane);
         if (PREC) {  // lo plane: what the fp16 rounding of the hi plane left over
@@ -328,7 +380,8 @@ __device__ __noinline__ float cdist_exact_d2(const float* __restrict__ a, const 
 }
 
 __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
-                                              int rows_valid, int col0, int ncols, float* stage, int lane) {
+                                              int rows_valid, int col0, int ncols, float* stage, int lane,
+                                              RowCtx* ts = nullptr) {
     const float na = row_ok ? __ldg(e.norm_a + row) : 0.f;
     float s32 = 0.f;  // 32 distances <= 2 each: an fp32 partial sum is exact to ~1e-7; fp64 only across chunks
     const bool full = ncols == 32;  // warp-uniform
@@ -364,7 +417,14 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
     }
     s32 = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     const double rs = row_ok ? (double)s32 : 0.0;
-    if (e.out_f != nullptr) {  // warp-uniform
+    if (e.out_f != nullptr && ts != nullptr && ts->tm_f != nullptr) {  // warp-uniform: tile leaves through TMA
+        // two 4 KB halves of the staging area alternate, so the store of chunk c overlaps the math of chunk c + 1
+        ts->flip ^= 1;
+        float* sp = stage + (ts->stage_bytes >= 8192 ? ts->flip * 1024 : 0);
+        ts_acquire(*ts, ts->stage_bytes >= 8192 ? (3u << (2 * ts->flip)) : 3u, lane);
+        stage_put_f32(sp, v, lane);
+        ts_issue(ts->tm_f, sp, col0, row - lane, lane);
+    } else if (e.out_f != nullptr) {  // warp-uniform
         stage_put_f32(stage, v, lane);
         float* wout = e.out_f + (row - lane) * e.ldo + col0;
         if (full && (e.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(wout) & 15) == 0)) {
@@ -385,11 +445,19 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // (Double-buffering the TMEM loads across chunks was measured SLOWER: 168 registers and less ILP in the GELU.)
 // PREC (single-CTA kernel only): the tile's sum lives in FOUR TMEM accumulators PACC columns apart (see gemm_tc_kernel);
 // they are added here in IEEE fp32.
-template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false, int PACC = 0>
+struct StoreMaps {
+    const CUtensorMap *f, *h, *a;
+    int stage_bytes;
+    uint32_t* pending;  // carried across the tiles of a warp
+    int* flip;
+};
+
+template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false, int PACC = 0, bool TS = false>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
-                                              const float* vec = nullptr, int vec_stride = 0, int cd_group = 0) {
+                                              const float* vec = nullptr, int vec_stride = 0, int cd_group = 0,
+                                              const StoreMaps* sm = nullptr) {
     const bool row_ok = row < args.M;
     const long long rv = (long long)args.M - (row - lane);
     const int rows_valid = rv > 32 ? 32 : (rv < 0 ? 0 : (int)rv);
@@ -403,6 +471,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
     rc.vec = vec;
     rc.vec_stride = vec_stride;
     rc.vec_col0 = col_first;
+    rc.tm_f = rc.tm_h = rc.tm_a = nullptr;
+    rc.pending = 0;
+    rc.stage_bytes = 4096;
+    rc.flip = 0;
+    if (TS && sm != nullptr) {
+        rc.tm_f = sm->f; rc.tm_h = sm->h; rc.tm_a = sm->a;
+        rc.stage_bytes = sm->stage_bytes;
+        rc.pending = *sm->pending;
+        rc.flip = *sm->flip;
+    }
 #pragma unroll 1
     for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
@@ -442,12 +520,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane);
-            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF, PREC>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
-            else epilogue_chunk<false, EF, PREC>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
+            if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane, TS ? &rc : nullptr);
+            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF, PREC, TS>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
+            else epilogue_chunk<false, EF, PREC, TS>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     rhave = rc.rhave;
+    if (TS && sm != nullptr) {
+        *sm->pending = rc.pending;
+        *sm->flip = rc.flip;
+    }
     // one writer per (column group, row): the row means come out bit-identical from run to run (no atomics)
     if (CDIST && row_ok) args.epi.row_part[(long long)cd_group * args.M + row] = (float)row_sum;
 }
@@ -624,25 +706,32 @@ struct Pair256 {
     // the mainloop is insensitive to 4 vs 5 vs 6 stages (measured, profiles/r01_gemm_probe_stages.log): 4 leaves room
     // for the epilogue buffers and, in the plain 8-warp variant, keeps the 196 KB carve-out (60 KB of L1)
     static constexpr int stages(int epi_warps, bool rpf) { return 4; }
-    static constexpr int smem_bytes(int epi_warps, bool rpf) {
-        return stages(epi_warps, rpf) * STAGE_BYTES + epi_warps * 4096 + resid_bytes(epi_warps, rpf) + vec_bytes(epi_warps) +
-               1024 + 256;
+    // staging area per epilogue warp: 4 KB fp32 tile (+ 2 KB 16-bit tile next to it in the 8-warp variants, so that a
+    // chunk's fp32 and 16-bit TMA stores do not wait for each other)
+    static constexpr int stage_bytes(int epi_warps, bool cdist) { return (epi_warps == 8 && !cdist) ? 6144 : 4096; }
+    static constexpr int smem_bytes(int epi_warps, bool rpf, bool cdist = false) {
+        return stages(epi_warps, rpf) * STAGE_BYTES + epi_warps * stage_bytes(epi_warps, cdist) + resid_bytes(epi_warps, rpf) +
+               vec_bytes(epi_warps) + 1024 + 256;
     }
 };
 
-template <int NEW, bool CDIST, bool RPF, int EF, bool PREC = false>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
+// TS: epilogue tiles leave through TMA stores (tmOutF / tmOutH / tmAux: fp32 output, 16-bit output, 16-bit aux_out).
+template <int NEW, bool CDIST, bool RPF, int EF, bool PREC = false, bool TS = false>  // NEW = epilogue warps (8 or 16); RPF = residual prefetch through smem
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmArgs args) {
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutH,
+                    const __grid_constant__ CUtensorMap tmAux, const GemmArgs args) {
     using Cfg = Pair256;
     constexpr int STAGES = Cfg::stages(NEW, RPF);
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096);
-    float* vec_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * 4096 + Cfg::resid_bytes(NEW, RPF) +
+    constexpr int SB = Cfg::stage_bytes(NEW, CDIST);  // staging bytes per epilogue warp
+    float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB);
+    float* vec_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF) +
                                                      Cfg::vec_bytes(NEW));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
@@ -754,6 +843,15 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int c0 = n2 * BN + h * HALF;
             return (r0 + 32 <= args.M && c0 + 32 <= args.N) ? args.epi.resid + r0 * args.epi.ldr + c0 : nullptr;
         };
+        uint32_t ts_pending = 0;
+        int ts_flip = 0;
+        StoreMaps smaps;
+        smaps.f = (TS && (eflags & (EPI_OUT_F32 | EPI_CDIST)) && args.epi.out_f != nullptr) ? &tmOutF : nullptr;
+        smaps.h = (TS && (eflags & EPI_OUT_H16)) ? &tmOutH : nullptr;
+        smaps.a = (TS && (eflags & EPI_SAVE_DGELU)) ? &tmAux : nullptr;
+        smaps.stage_bytes = SB;
+        smaps.pending = &ts_pending;
+        smaps.flip = &ts_flip;
         bool rhave = false;
         if (want_pf) {
             const float* src = tile_src(pair_id);
@@ -791,10 +889,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<HALF / 32, true, CDIST, EF, PREC>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
-                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * 1024,
-                                           row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h);
+            epilogue_tile<HALF / 32, true, CDIST, EF, PREC, 0, TS>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+                                           n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * (SB / 4),
+                                           row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h, &smaps);
         }
+        if (TS && lane == 0) bulk_wait_all();  // this warp's bulk stores have left shared memory and are globally visible
     }
     tc_fence_before();
     cluster_sync_all();
@@ -993,13 +1092,50 @@ static int launch_tc(cudaStream_t st, const GemmOperand& A, const GemmOperand& B
     return (args.epi.flags & EPI_CDIST) ? launch_tc_impl<BN, true>(st, A, B, args) : launch_tc_impl<BN, false>(st, A, B, args);
 }
 
-template <int NEW, bool CDIST, bool RPF = false, int EF = -1, bool PREC = false>
+// 2-D map over an (rows x cols, leading dimension ld) output for TMA stores of 32 x 32 boxes in the staging swizzle
+static int make_store_map(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    NB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    const size_t el = f32 ? 4 : 2;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * el};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim,
+                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed (%d): rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return 0;
+}
+// can every output of this epilogue leave through TMA?  (16-byte aligned base and pitch, one batch)
+// Measured on the bench step (profiles/r02_tma_store_ab.txt, alternating runs in one box): TMA stores gain 2-6 % where
+// the epilogue only emits one 16-bit tile per chunk and has no LayerNorm algebra (conv1-6, QKV) and on the distance
+// matrix; they LOSE 3-5 % on the residual epilogues (out-proj, FC2: the fence + wait per chunk serialises warps that
+// are already latency-bound on the residual stream) and on FC1.  NOMAD_B200_TMA_STORE: 0 = never, 1 = where it wins
+// (default), 2 = every epilogue that can.
+static bool tma_store_ok(const GemmArgs& args) {
+    static const int enabled = getenv("NOMAD_B200_TMA_STORE") ? atoi(getenv("NOMAD_B200_TMA_STORE")) : 1;
+    const GemmEpilogue& e = args.epi;
+    if (!enabled || args.batch != 1 || (e.flags & EPI_PRECISE)) return false;
+    if (enabled == 1 && ((e.flags & (EPI_RESID | EPI_RESID_LN | EPI_SAVE_DGELU | EPI_MUL_AUX)) ||
+                         ((e.flags & EPI_LN_FOLD) && (e.flags & EPI_GELU))))
+        return false;
+    auto ok = [&](const void* p, size_t el) { return p != nullptr && ((uintptr_t)p & 15) == 0 && (e.ldo * el) % 16 == 0; };
+    if ((e.flags & EPI_CDIST) && e.out_f != nullptr && !ok(e.out_f, 4)) return false;
+    if ((e.flags & EPI_OUT_F32) && !ok(e.out_f, 4)) return false;
+    if ((e.flags & EPI_OUT_H16) && !ok(e.out_h, 2)) return false;
+    if ((e.flags & EPI_SAVE_DGELU) && !ok(e.aux_out, 2)) return false;
+    return true;
+}
+
+template <int NEW, bool CDIST, bool RPF = false, int EF = -1, bool PREC = false, bool TS = true>
 static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, GemmArgs& args) {
     using Cfg = Pair256;
-    constexpr int SMEM = Cfg::smem_bytes(NEW, RPF);
+    if (TS && !tma_store_ok(args)) return launch_pair_impl<NEW, CDIST, RPF, EF, PREC, false>(st, A, B, args);
+    constexpr int SMEM = Cfg::smem_bytes(NEW, RPF, CDIST);
     static bool attr_set[64] = {false};  // the attribute is per device
     if (bool* flag = device_once_flag(attr_set)) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        NB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         *flag = true;
     }
     CUtensorMap tmA, tmB, tmA2, tmB2;
@@ -1017,7 +1153,14 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, args);
+    CUtensorMap tmF = tmA, tmH = tmA, tmX = tmA;  // placeholders when an output is absent
+    if (TS) {
+        const GemmEpilogue& e = args.epi;
+        if ((e.flags & (EPI_OUT_F32 | EPI_CDIST)) && e.out_f) NB_TRY(make_store_map(&tmF, e.out_f, true, args.M, args.N, e.ldo));
+        if (e.flags & EPI_OUT_H16) NB_TRY(make_store_map(&tmH, e.out_h, false, args.M, args.N, e.ldo));
+        if (e.flags & EPI_SAVE_DGELU) NB_TRY(make_store_map(&tmX, e.aux_out, false, args.M, args.N, e.ldo));
+    }
+    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args);
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
