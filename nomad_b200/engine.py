@@ -193,6 +193,45 @@ class Engine:
                                                       hp(dm_host), hp(mean_host), wp, wbytes, _stream_ptr()),
                        "nomad_b200_score_host")
 
+    # ------------------------------------------------------------------ pinned staging ring
+    def pinned(self, nbytes: int) -> torch.Tensor:
+        """A pinned host staging buffer (ring of 3, grow-only) that no in-flight H2D copy is still reading; after
+        issuing the copy call :meth:`pinned_release` so the slot is fenced by an event on the current stream."""
+        if not hasattr(self, "_ring"):
+            self._ring, self._ring_ev, self._ring_i = [None] * 3, [None] * 3, 0
+        self._ring_i = (self._ring_i + 1) % 3
+        i = self._ring_i
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()
+        if self._ring[i] is None or self._ring[i].numel() < nbytes:
+            self._ring[i] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+        return self._ring[i]
+
+    def pinned_release(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._ring_ev[self._ring_i] = ev
+
+    def embed_pcm16_mono(self, pcms: Sequence[np.ndarray], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """A batch of 16 kHz MONO 16-bit PCM utterances (1-D int16 arrays): packed into ONE pinned buffer, ONE H2D copy
+        of the 16-bit samples, ONE conversion launch (``nomad_b200_ingest_pcm16`` over the concatenation: the
+        conversion is per sample) and one ``nomad_b200_embed`` -- instead of a copy + a launch per file."""
+        lens = [int(p.shape[0]) for p in pcms]
+        total = sum(lens)
+        stage = self.pinned(2 * total)
+        host = stage[: 2 * total].view(torch.int16).numpy()
+        o = 0
+        for p, n in zip(pcms, lens):
+            host[o:o + n] = p
+            o += n
+        dev = stage[: 2 * total].view(torch.int16).to(self.device, non_blocking=True)
+        self.pinned_release()
+        wav = torch.empty((total,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_ingest_pcm16(_ptr(dev), total, 1, 16000, 16000, 0, _ptr(wav), _stream_ptr()),
+                       "nomad_b200_ingest_pcm16")
+        return self.embed_packed(wav, self.offsets(lens), out)
+
     # ------------------------------------------------------------------ ingest
     def ingest_pcm16(self, pcm: np.ndarray, sr: int, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
         """``load_processing`` on the device: (n_frames, channels) or (n_frames,) int16 HOST samples at ``sr`` ->
@@ -256,8 +295,10 @@ class Engine:
         return loss, grad
 
     # ------------------------------------------------------------------ distance
-    def cdist_mean(self, deg: torch.Tensor, nmr: torch.Tensor, want_matrix: bool = True, gemm_impl: int = 0):
-        """(n, 256), (m, 256) fp32 CUDA -> ((n, m) fp32 | None, (n,) fp64 row means)."""
+    def cdist_mean(self, deg: torch.Tensor, nmr: torch.Tensor, want_matrix: bool = True, gemm_impl: int = 0,
+                   out_dm: Optional[torch.Tensor] = None, out_mean: Optional[torch.Tensor] = None):
+        """(n, 256), (m, 256) fp32 CUDA -> ((n, m) fp32 | None, (n,) fp64 row means); ``out_dm`` / ``out_mean``:
+        caller-owned result tensors (a scoring service reuses them across batches)."""
         deg = deg.to(self.device, torch.float32).contiguous()
         nmr = nmr.to(self.device, torch.float32).contiguous()
         if deg.dim() != 2 or nmr.dim() != 2 or deg.shape[1] != EMB_DIM or nmr.shape[1] != EMB_DIM:
@@ -265,8 +306,12 @@ class Engine:
             raise ValueError(f"cdist_mean needs (n, {EMB_DIM}) and (m, {EMB_DIM}) embeddings, got {tuple(deg.shape)} "
                              f"and {tuple(nmr.shape)}")
         n, m = deg.shape[0], nmr.shape[0]
-        dm = torch.empty((n, m), dtype=torch.float32, device=self.device) if want_matrix else None
-        mean = torch.empty((n,), dtype=torch.float64, device=self.device)
+        dm = None
+        if want_matrix:
+            dm = out_dm if out_dm is not None else torch.empty((n, m), dtype=torch.float32, device=self.device)
+            assert dm.shape == (n, m) and dm.dtype == torch.float32 and dm.is_contiguous() and dm.device == self.device
+        mean = out_mean if out_mean is not None else torch.empty((n,), dtype=torch.float64, device=self.device)
+        assert mean.shape == (n,) and mean.dtype == torch.float64 and mean.device == self.device
         need = self.lib.nomad_b200_cdist_workspace_bytes(n, m)
         ws = self.workspace(need)
         wp, wbytes = self._aligned(ws)

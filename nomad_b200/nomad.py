@@ -180,6 +180,7 @@ class Nomad():
         self.max_batch_samples = int(max_batch_seconds * 16000)
         self.device_ingest = os.environ.get("NOMAD_B200_DEVICE_INGEST", "1") != "0"
         self.window_files = int(os.environ.get("NOMAD_B200_WINDOW_FILES", "4096"))
+        self.reader_threads = int(os.environ.get("NOMAD_B200_READER_THREADS", str(min(16, os.cpu_count() or 4))))
 
     def predict(self, mode='dir', nmr='data/nmr-data', deg='data/test-data', results_path=None):
         if nmr is None:
@@ -292,33 +293,56 @@ class Nomad():
             out[torch.as_tensor(idx, device=self.engine.device)] = emb
         return out.cpu().numpy()
 
+    def _read_for_embed(self, filepath):
+        """One file of the per-file loop -> ("pcm", int16 (n,)) for the common case (16-bit PCM, mono, 16 kHz: the
+        samples cross PCIe as 16-bit and are converted on the GPU in one launch per batch) or ("wav", (1, N) tensor)."""
+        if isinstance(filepath, np.ndarray):
+            filepath = filepath[0]  # nomad.py:194-195: a DataFrame row
+        if self.device_ingest:
+            got = audio.read_pcm16(filepath)
+            if got is not None:
+                pcm, sr = got
+                if sr == 16000 and pcm.shape[1] == 1:
+                    return "pcm", pcm[:, 0]
+                return "dev", (pcm, sr)   # other rates / stereo: per-file device ingest (mix + resample on the GPU)
+        return "wav", self.load_processing(filepath, trim=False)
+
     def embed_files(self, filepaths: Sequence, root=False) -> torch.Tensor:
         """The reference's per-file loop (``nomad.py:172-186``) restructured for throughput -> (n, 256) CUDA tensor in
-        input order.  Files are read in windows of ``self.window_files`` (bounded memory for 100 k-file corpora),
-        every window is length-bucketed into batches, and the GPU works on window k while the host reads window
-        k + 1 (no per-batch synchronisation; the returned tensor may still be being computed)."""
+        input order.  Files are read in windows of ``self.window_files`` (bounded memory for 100 k-file corpora) by a
+        small thread pool, every window is length-bucketed into batches, and the GPU works on window k while the host
+        reads window k + 1 (no per-batch synchronisation; the returned tensor may still be being computed)."""
+        from concurrent.futures import ThreadPoolExecutor
         n_files = len(filepaths)
         parts = []
-        for w0 in range(0, n_files, self.window_files):
-            waves = []
-            for filename_anchor in filepaths[w0:w0 + self.window_files]:
-                if root:
-                    filepath = os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0])
-                else:
-                    filepath = filename_anchor
-                # 16-bit PCM wavs are converted / mixed / resampled on the GPU (nomad_b200_ingest_pcm16); same result
-                # as the host ``load_processing`` below, which every other format still takes
-                wave = (audio.load_processing_device(self.engine, filepath, trim=False) if self.device_ingest
-                        else self.load_processing(filepath, trim=False))
-                if wave.shape[-1] < MIN_SAMPLES:
-                    raise RuntimeError(f"Calculated padded input size per channel: ({wave.shape[-1]}). Kernel size: (10). "
-                                       "Kernel size can't be greater than actual input size")
-                waves.append(wave.reshape(-1))
-            lengths = [int(w.numel()) for w in waves]
-            dev_out = torch.empty((len(waves), EMB_DIM), dtype=torch.float32, device=self.engine.device)
-            for idx in plan_batches(lengths, self.max_batch_samples):
-                dev_out[torch.as_tensor(idx, device=self.engine.device)] = self.engine.embed([waves[i] for i in idx])
-            parts.append(dev_out)  # still being computed; the host goes on reading the next window
+        with ThreadPoolExecutor(max_workers=self.reader_threads) as pool:
+            for w0 in range(0, n_files, self.window_files):
+                paths = []
+                for filename_anchor in filepaths[w0:w0 + self.window_files]:
+                    if root:
+                        paths.append(os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0]))
+                    else:
+                        paths.append(filename_anchor)
+                items = list(pool.map(self._read_for_embed, paths))
+                lengths = []
+                for k, (kind, v) in enumerate(items):
+                    if kind == "dev":   # 16-bit PCM at another rate / stereo: mix + resample on the GPU, per file
+                        items[k] = (kind, v) = ("wav", self.engine.ingest_pcm16(v[0], v[1], 16000, False))
+                    n = int(v.shape[-1]) if kind == "wav" else int(v.shape[0])
+                    if n < MIN_SAMPLES:
+                        raise RuntimeError(f"Calculated padded input size per channel: ({n}). Kernel size: (10). "
+                                           "Kernel size can't be greater than actual input size")
+                    lengths.append(n)
+                dev_out = torch.empty((len(items), EMB_DIM), dtype=torch.float32, device=self.engine.device)
+                for idx in plan_batches(lengths, self.max_batch_samples):
+                    sel = torch.as_tensor(idx, device=self.engine.device)
+                    if all(items[i][0] == "pcm" for i in idx):
+                        dev_out[sel] = self.engine.embed_pcm16_mono([items[i][1] for i in idx])
+                    else:
+                        waves = [items[i][1].reshape(-1) if items[i][0] == "wav"
+                                 else torch.from_numpy(items[i][1].astype(np.float32) / 32768.0) for i in idx]
+                        dev_out[sel] = self.engine.embed(waves)
+                parts.append(dev_out)  # still being computed; the host goes on reading the next window
         if not parts:
             return torch.zeros((0, EMB_DIM), dtype=torch.float32, device=self.engine.device)
         return torch.cat(parts) if len(parts) > 1 else parts[0]
