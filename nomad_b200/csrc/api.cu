@@ -734,6 +734,9 @@ int nomad_b200_destroy(nomad_b200_handle* hh) {
     cudaSetDevice(hh->h.device);
     cudaDeviceSynchronize();
     for (void* p : hh->h.allocs) cudaFree(p);
+    for (auto& e : hh->h.loss_graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (hh->h.graph_stream) cudaStreamDestroy(hh->h.graph_stream);
     if (hh->h.meta_host) cudaFreeHost(hh->h.meta_host);
     if (hh->h.copy_stream) {
         cudaStreamDestroy(hh->h.copy_stream);

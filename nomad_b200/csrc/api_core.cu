@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace nb
 

@@ -44,6 +44,7 @@ const char* get_error();
 
 // every kernel launch of the library goes through this so bench.py can report gpu_launches
 void count_launch();
+void count_launches(long long n);  // graph replays: n kernels at once
 #define NB_LAUNCHED()                 \
     do {                              \
         nb::count_launch();           \

@@ -1015,6 +1015,7 @@ void gemm_profile_enable(bool on) {
     g_prof.used = 0;
     g_prof.flops.clear();
 }
+bool gemm_profile_active() { return g_prof.on; }
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
     double ms = 0.0, fl = 0.0;
     for (size_t i = 0; i < g_prof.used; ++i) {

@@ -92,6 +92,7 @@ int cdist_row_groups(long long n, long long m);
 
 // event-pair timing of every tensor-core GEMM launch while enabled (see bench.py)
 void gemm_profile_enable(bool on);
+bool gemm_profile_active();
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 
 }  // namespace nb

@@ -543,7 +543,8 @@ using namespace nb;
 
 extern "C" {
 
-size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
+// core workspace of one loss step (forward in save mode + backward buffers), without the CUDA-graph staging area
+static size_t loss_core_bytes(int B, int64_t N, int with_grad) {
     Plan p;
     if (loss_plan(B, N, &p)) return 0;
     const size_t fwd = carve_workspace(p, nullptr, nullptr, true);
@@ -551,17 +552,23 @@ size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
     const long long pos_rows_e = frames_e + (long long)POS_GAP * B + POS_K / 2;
     return fwd + carve_loss(p, B, frames_e, rows0_e, pos_rows_e, with_grad != 0, nullptr, nullptr) + 2048;
 }
+static size_t loss_stage_bytes(int B, int64_t N) { return ((size_t)3 * B * N * 4 + 4096 + 1023) / 1024 * 1024; }
 
-int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const float* clean_dev, int B, int64_t N,
-                            float feature_grad_mult, float* loss_dev, float* d_est_dev, void* workspace_dev,
-                            size_t workspace_bytes, void* stream) {
-    NB_CHECK(hh != nullptr, "null nomad_b200 handle");
+size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
+    const size_t core = loss_core_bytes(B, N, with_grad);
+    if (core == 0) return 0;
+    // + estimate / clean / gradient / loss staging: the step is replayed as a CUDA graph over fixed addresses
+    return (core + 1023) / 1024 * 1024 + loss_stage_bytes(B, N);
+}
+
+}  // extern "C"
+
+// phase 0: the whole step; 1: only the per-call metadata upload (the part of a step that cannot live in a CUDA graph:
+// it goes through the handle's pinned staging ring); 2: the whole step except that upload (what the graph holds)
+static int loss_run(nomad_b200_handle* hh, const float* est_dev, const float* clean_dev, int B, int64_t N,
+                    float feature_grad_mult, float* loss_dev, float* d_est_dev, void* workspace_dev, size_t workspace_bytes,
+                    cudaStream_t st, int phase) {
     Handle* h = &hh->h;
-    NB_CHECK(est_dev && clean_dev && loss_dev && workspace_dev, "loss: null pointer");
-    NB_CHECK(h->has_loss_head, "loss: call nomad_b200_set_loss_head first (LossNetLayers has its own head, nomad.py:238-241)");
-    NB_CHECK((((uintptr_t)est_dev | (uintptr_t)clean_dev) & 3) == 0, "loss: waveform pointers must be 4-byte aligned");
-    NB_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
     const bool with_grad = d_est_dev != nullptr;
     const Weights& w = h->w;
     const int impl = h->gemm_impl;
@@ -586,7 +593,8 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
     NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "loss: workspace must be 1024-byte aligned");
 
     // ------------------------------------------------------------------ forward (both halves, save mode)
-    NB_TRY(upload_meta(h, p, ws, st));
+    if (phase != 2) NB_TRY(upload_meta(h, p, ws, st));
+    if (phase == 1) return 0;
     NB_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * 16, st));
     NB_TRY(forward_encoder(h, p, ws, est_dev, st, nullptr, 0));
     NB_TRY(launch_pool_head(st, ws.x, ws.meta, p.B, w.loss_head_wt, w.loss_head_b, L.emb, L.pooled));
@@ -729,6 +737,84 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
     dim3 fgrid((unsigned)((N + 255) / 256), B);
     conv0_bwd_finish_kernel<<<fgrid, 256, 0, st>>>(L.c0_V, est_dev, ws.meta, L.c0_consts, N, 1.0f / S, d_est_dev);
     NB_LAUNCHED();
+    return 0;
+}
+
+extern "C" {
+
+// The step is ~250 small launches for B = 32 x 2 s (profiles/r02_loss_trace_before.log: 8 % of the step was launch gaps):
+// after one eager call per (B, N, grad, feature_grad_mult, workspace) the launch sequence is captured into a CUDA graph
+// over fixed addresses -- inputs are copied into a staging area at the end of the caller's workspace, results copied
+// out -- and replayed.  NOMAD_B200_LOSS_GRAPH=0 keeps every call eager.
+int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const float* clean_dev, int B, int64_t N,
+                            float feature_grad_mult, float* loss_dev, float* d_est_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream) {
+    NB_CHECK(hh != nullptr, "null nomad_b200 handle");
+    Handle* h = &hh->h;
+    NB_CHECK(est_dev && clean_dev && loss_dev && workspace_dev, "loss: null pointer");
+    NB_CHECK(h->has_loss_head, "loss: call nomad_b200_set_loss_head first (LossNetLayers has its own head, nomad.py:238-241)");
+    NB_CHECK((((uintptr_t)est_dev | (uintptr_t)clean_dev) & 3) == 0, "loss: waveform pointers must be 4-byte aligned");
+    NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "loss: workspace must be 1024-byte aligned");
+    NB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int with_grad = d_est_dev != nullptr ? 1 : 0;
+    static const int use_graph = getenv("NOMAD_B200_LOSS_GRAPH") ? atoi(getenv("NOMAD_B200_LOSS_GRAPH")) : 1;
+    const size_t core = (loss_core_bytes(B, N, with_grad) + 1023) / 1024 * 1024;
+    NB_CHECK(core != 0, "loss: %s", nomad_b200_last_error());
+    const bool graph_ok = use_graph && h->gemm_impl == 0 && !getenv("NOMAD_B200_DEBUG_LOSS") && !gemm_profile_active() &&
+                          workspace_bytes >= core + loss_stage_bytes(B, N);
+    if (!graph_ok)
+        return loss_run(hh, est_dev, clean_dev, B, N, feature_grad_mult, loss_dev, d_est_dev, workspace_dev, workspace_bytes, st, 0);
+
+    const size_t bn = (size_t)B * N;
+    float* s_est = (float*)((char*)workspace_dev + core);
+    float* s_clean = s_est + bn;
+    float* s_grad = s_clean + bn;
+    float* s_loss = s_grad + bn;
+    NB_CUDA(cudaMemcpyAsync(s_est, est_dev, bn * 4, cudaMemcpyDeviceToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(s_clean, clean_dev, bn * 4, cudaMemcpyDeviceToDevice, st));
+    LossGraphEntry* ent = nullptr;
+    for (auto& e : h->loss_graphs)
+        if (e.B == B && e.N == N && e.with_grad == with_grad && e.fgm == feature_grad_mult && e.ws == workspace_dev) ent = &e;
+    if (ent == nullptr) {  // first call with this shape: eager (also performs the one-off per-kernel attribute set-up)
+        if (h->loss_graphs.size() >= 8) {
+            for (auto& e : h->loss_graphs)
+                if (e.exec) cudaGraphExecDestroy(e.exec);
+            h->loss_graphs.clear();
+        }
+        h->loss_graphs.push_back(LossGraphEntry{B, (long long)N, with_grad, feature_grad_mult, workspace_dev, nullptr, 0, false});
+        NB_TRY(loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev, core, st, 0));
+    } else if (ent->exec == nullptr && !ent->failed) {  // second call: capture on the handle's own stream, then launch
+        if (!h->graph_stream) NB_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+        NB_TRY(loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev, core, st, 1));
+        const long long n0 = nomad_b200_launch_count();
+        cudaGraph_t graph = nullptr;
+        NB_CUDA(cudaStreamBeginCapture(h->graph_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev,
+                                core, h->graph_stream, 2);
+        const cudaError_t ce = cudaStreamEndCapture(h->graph_stream, &graph);
+        ent->kernels = nomad_b200_launch_count() - n0;
+        if (rc == 0 && ce == cudaSuccess && graph != nullptr &&
+            cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
+            cudaGraphDestroy(graph);
+            NB_CUDA(cudaGraphLaunch(ent->exec, st));
+        } else {  // capture not possible here: stay eager for this shape
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ent->exec = nullptr;
+            ent->failed = true;
+            count_launches(-ent->kernels);
+            NB_TRY(loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev, core, st, 2));
+        }
+    } else if (ent->exec != nullptr) {
+        NB_TRY(loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev, core, st, 1));
+        NB_CUDA(cudaGraphLaunch(ent->exec, st));
+        count_launches(ent->kernels);
+    } else {
+        NB_TRY(loss_run(hh, s_est, s_clean, B, N, feature_grad_mult, s_loss, with_grad ? s_grad : nullptr, workspace_dev, core, st, 0));
+    }
+    NB_CUDA(cudaMemcpyAsync(loss_dev, s_loss, 4, cudaMemcpyDeviceToDevice, st));
+    if (with_grad) NB_CUDA(cudaMemcpyAsync(d_est_dev, s_grad, bn * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -137,6 +137,18 @@ struct Workspace {
     size_t bytes;
 };
 
+// one captured loss step (loss.cu): replayed while shape, gradient request and workspace stay the same
+struct LossGraphEntry {
+    int B;
+    long long N;
+    int with_grad;
+    float fgm;
+    void* ws;
+    cudaGraphExec_t exec;
+    long long kernels;  // kernel launches the graph replays (for nomad_b200_launch_count)
+    bool failed;        // capture was refused once: this shape stays eager
+};
+
 struct Handle {
     int device = 0;
     int gemm_impl = 0;
@@ -149,6 +161,8 @@ struct Handle {
     size_t meta_cap = 0;        // bytes per staging slot
     int meta_slot = 0;          // staging slot of the most recent call
     cudaEvent_t meta_event = nullptr;  // last use of meta_host by an async copy
+    std::vector<LossGraphEntry> loss_graphs;
+    cudaStream_t graph_stream = nullptr;  // capture stream of the loss-step graphs (capture is not legal on stream 0)
     cudaStream_t copy_stream = nullptr;  // H2D side stream of the *_host entry points
     cudaEvent_t fork_event = nullptr;
     cudaEvent_t copied[8] = {};

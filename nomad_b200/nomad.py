@@ -179,7 +179,7 @@ class Nomad():
         self.feature_grad_mult = float(feature_grad_mult)
         self.max_batch_samples = int(max_batch_seconds * 16000)
         self.device_ingest = os.environ.get("NOMAD_B200_DEVICE_INGEST", "1") != "0"
-        self.window_files = int(os.environ.get("NOMAD_B200_WINDOW_FILES", "4096"))
+        self.window_files = int(os.environ.get("NOMAD_B200_WINDOW_FILES", "1024"))
         self.reader_threads = int(os.environ.get("NOMAD_B200_READER_THREADS", str(min(16, os.cpu_count() or 4))))
 
     def predict(self, mode='dir', nmr='data/nmr-data', deg='data/test-data', results_path=None):
