@@ -18,6 +18,7 @@
 // epilogues were all measured and bought nothing (profiles/r01_attention_notes.md) -- so the design goes for
 // occupancy instead: small tiles let three CTAs (12 softmax warps) share an SM and fill each other's gaps.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -99,6 +100,8 @@ __device__ __forceinline__ FaItem fa_item(const AttnFaArgs& a, int i) {
     return it;
 }
 
+// P2: packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2) in the softmax warps -- 12 instead of 16 issue slots per 4 scores
+template <bool P2>
 __global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                     const AttnFaArgs args) {
@@ -264,8 +267,18 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                             uint32_t r[32];
                             tmem_ld_32x32(trow + FA_O_COL + c * 32, r);
                             tmem_ld_wait();
+                            if (P2) {
+                                const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * sc);
+                                for (int k = 0; k < 32; k += 2) {
+                                    const float2 t = fmul2(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), sc2);
+                                    r[k] = __float_as_uint(t.x);
+                                    r[k + 1] = __float_as_uint(t.y);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * sc);
+                            }
                             tmem_st_32x32(trow + FA_O_COL + c * 32, r);
                         }
                         tmem_st_wait();
@@ -277,7 +290,20 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                         tmem_ld_32x32(trow + c * 32, r);
                         tmem_ld_wait();
                         float p[32];
-                        if (c * 32 + 32 <= nv) {
+                        if (P2 && c * 32 + 32 <= nv) {
+                            const float2 l2 = make_float2(LOG2E, LOG2E), nms = make_float2(-ms, -ms);
+                            float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4) {
+                                const float2 e0 = ffma2(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), l2, nms);
+                                const float2 e1 = ffma2(make_float2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])), l2, nms);
+                                p[k] = ex2_approx(e0.x); p[k + 1] = ex2_approx(e0.y);
+                                p[k + 2] = ex2_approx(e1.x); p[k + 3] = ex2_approx(e1.y);
+                                a0 = fadd2(a0, make_float2(p[k], p[k + 1]));
+                                a1 = fadd2(a1, make_float2(p[k + 2], p[k + 3]));
+                            }
+                            sum += (a0.x + a0.y) + (a1.x + a1.y);
+                        } else if (c * 32 + 32 <= nv) {
                             float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int k = 0; k < 32; ++k) {
@@ -326,8 +352,18 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                     tmem_ld_32x32(trow + FA_O_COL + c * 32, r);
                     tmem_ld_wait();
                     float v[32];
+                    if (P2) {
+                        const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) * inv;
+                        for (int k = 0; k < 32; k += 2) {
+                            const float2 t = fmul2(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), inv2);
+                            v[k] = t.x;
+                            v[k + 1] = t.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) * inv;
+                    }
                     stage_put_h16(stage, v, lane);
                     stage_flush_h16(stage, wout + c * 32, EMBED, rv, 32, lane);
                 }
@@ -383,9 +419,11 @@ int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items,
     NB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     static bool attr_set[64] = {false};  // the attribute is per device
     if (bool* flag = device_once_flag(attr_set)) {
-        NB_CUDA(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        NB_CUDA(cudaFuncSetAttribute(attention_fa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        NB_CUDA(cudaFuncSetAttribute(attention_fa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         *flag = true;
     }
+    static const int packed = getenv("NOMAD_B200_FA_F32X2") ? atoi(getenv("NOMAD_B200_FA_F32X2")) : 1;
     if (n_items <= 0) return 0;
     CUtensorMap tmq, tmkv;
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * EMBED), (cuuint64_t)frames};
@@ -402,7 +440,8 @@ int launch_attention_fa(cudaStream_t st, const op_t* qkv, const uint32_t* items,
     const long long total = (long long)n_items * HEADS;
     int grid = FA_CTAS_PER_SM * device_sm_count();
     if (total < grid) grid = (int)total;
-    attention_fa_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmq, tmkv, a);
+    if (packed) attention_fa_kernel<true><<<grid, FA_THREADS, FA_SMEM, st>>>(tmq, tmkv, a);
+    else attention_fa_kernel<false><<<grid, FA_THREADS, FA_SMEM, st>>>(tmq, tmkv, a);
     NB_LAUNCHED();
     return 0;
 }

@@ -125,6 +125,28 @@ __device__ __forceinline__ float gelu_fast(float x) {
     const float e = ex2_approx(x * p);
     return x * rcp_approx(1.0f + e);
 }
+// gelu_fast on a register pair with packed fp32 arithmetic: 6 packed + 2 FMNMX + 4 MUFU for two values instead of
+// 2 x (7 + 2) scalar instructions (the GELU epilogues are bound by instruction issue)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c);
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b);
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b);
+#ifndef NB_F32X2
+#define NB_F32X2 1   // 0: scalar fp32 arithmetic in the GELU / LayerNorm-fold epilogues (A/B builds)
+#endif
+__device__ __forceinline__ float gelu_fast(float x);
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+#if !NB_F32X2
+    return make_float2(gelu_fast(x.x), gelu_fast(x.y));
+#endif
+    float2 x2 = fmul2(x, x);
+    x2.x = fminf(x2.x, 36.0f);
+    x2.y = fminf(x2.y, 36.0f);
+    float2 p = ffma2(make_float2(1.0142630552e-03f, 1.0142630552e-03f), x2, make_float2(-1.0677572400e-01f, -1.0677572400e-01f));
+    p = ffma2(p, x2, make_float2(-2.3011213395e+00f, -2.3011213395e+00f));
+    const float2 u = fmul2(x, p);
+    const float2 e = fadd2(make_float2(ex2_approx(u.x), ex2_approx(u.y)), make_float2(1.0f, 1.0f));
+    return fmul2(x, make_float2(rcp_approx(e.x), rcp_approx(e.y)));
+}
 __device__ __forceinline__ float gelu_act(float x) {
 #if NB_GELU_FAST
     return gelu_fast(x);
@@ -154,6 +176,37 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+// Packed fp32 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two fp32 operations per issued instruction).  The softmax and
+// epilogue warps of this library are bound by instruction issue, not by a pipe, so halving their FMA-pipe instruction
+// count is a direct gain.  Operands are register pairs; adjacent registers pack for free.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -178,14 +231,32 @@ __device__ __forceinline__ float2 unpack_op(uint32_t u) {
 // of fp16 tanh (~5e-4 absolute on t, i.e. <= 2.5e-4 |x| on the result): about one extra fp16 rounding.  Only used
 // where the MUFU pipe is the bound and the result is stored as fp16 anyway (conv0: 1.7 G activations per step).
 __device__ __forceinline__ uint32_t gelu_pair_h2(float x0, float x1) {
-    const float a0 = fminf(x0 * x0, 36.0f), a1 = fminf(x1 * x1, 36.0f);
-    float p0 = fmaf(-3.515167885e-04f, a0, 3.700564602e-02f), p1 = fmaf(-3.515167885e-04f, a1, 3.700564602e-02f);
-    p0 = fmaf(p0, a0, 7.975078843e-01f);
-    p1 = fmaf(p1, a1, 7.975078843e-01f);
-    const uint32_t u = pack_op(x0 * p0, x1 * p1);
+#if !NB_F32X2
+    {
+        const float a0 = fminf(x0 * x0, 36.0f), a1 = fminf(x1 * x1, 36.0f);
+        float p0 = fmaf(-3.515167885e-04f, a0, 3.700564602e-02f), p1 = fmaf(-3.515167885e-04f, a1, 3.700564602e-02f);
+        p0 = fmaf(p0, a0, 7.975078843e-01f);
+        p1 = fmaf(p1, a1, 7.975078843e-01f);
+        const uint32_t u = pack_op(x0 * p0, x1 * p1);
+        uint32_t t;
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+        const uint32_t hx = pack_op(0.5f * x0, 0.5f * x1);
+        uint32_t r;
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(hx), "r"(t));
+        return r;
+    }
+#endif
+    const float2 x = make_float2(x0, x1);
+    float2 a = fmul2(x, x);
+    a.x = fminf(a.x, 36.0f);
+    a.y = fminf(a.y, 36.0f);
+    float2 p = ffma2(make_float2(-3.515167885e-04f, -3.515167885e-04f), a, make_float2(3.700564602e-02f, 3.700564602e-02f));
+    p = ffma2(p, a, make_float2(7.975078843e-01f, 7.975078843e-01f));
+    const float2 xp = fmul2(x, p), hxf = fmul2(x, make_float2(0.5f, 0.5f));
+    const uint32_t u = pack_op(xp.x, xp.y);
     uint32_t t;
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
-    const uint32_t hx = pack_op(0.5f * x0, 0.5f * x1);
+    const uint32_t hx = pack_op(hxf.x, hxf.y);
     uint32_t r;
     asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(hx), "r"(t));
     return r;

@@ -195,10 +195,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
                 const float4 a = sv ? *reinterpret_cast<const float4*>(rc.vec + rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
                                     : __ldg(sp + j);
                 const float4 c = sv ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j) : __ldg(cp + j);
+#if NB_F32X2
+                const float2 nm2 = make_float2(nm, nm), rs2 = make_float2(rs, rs);
+                const float2 lo = ffma2(rs2, ffma2(nm2, make_float2(a.x, a.y), make_float2(v[4 * j + 0], v[4 * j + 1])), make_float2(c.x, c.y));
+                const float2 hi = ffma2(rs2, ffma2(nm2, make_float2(a.z, a.w), make_float2(v[4 * j + 2], v[4 * j + 3])), make_float2(c.z, c.w));
+                v[4 * j + 0] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi.x; v[4 * j + 3] = hi.y;
+#else
                 v[4 * j + 0] = fmaf(rs, fmaf(nm, a.x, v[4 * j + 0]), c.x);
                 v[4 * j + 1] = fmaf(rs, fmaf(nm, a.y, v[4 * j + 1]), c.y);
                 v[4 * j + 2] = fmaf(rs, fmaf(nm, a.z, v[4 * j + 2]), c.z);
                 v[4 * j + 3] = fmaf(rs, fmaf(nm, a.w, v[4 * j + 3]), c.w);
+#endif
             }
         }
     }
@@ -217,8 +224,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             stage_flush_h16(reinterpret_cast<op_t*>(stage), e.aux_out + woff, e.ldo, rows_valid, ncols, lane);
         }
     } else if (flags & EPI_GELU) {
+        if (PREC || !NB_GELU_FAST) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = PREC ? gelu_erf_exact(v[j]) : gelu_act(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = PREC ? gelu_erf_exact(v[j]) : gelu_act(v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float2 t = gelu_fast2(make_float2(v[j], v[j + 1]));
+                v[j] = t.x;
+                v[j + 1] = t.y;
+            }
+        }
     }
     if ((FULL || row_ok) && (flags & EPI_MUL_AUX)) {
         const uint4* ap = reinterpret_cast<const uint4*>(e.aux + off);
