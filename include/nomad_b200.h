@@ -155,6 +155,24 @@ NOMAD_B200_API int nomad_b200_write_scores_csv(const char* path, const char* ind
  * device. */
 NOMAD_B200_API int nomad_b200_paired_dist(const float* a_dev, const float* b_dev, int64_t n, double* out_dev, void* stream);
 
+/* ---- triplet fine-tuning step (reference src/training/train_triplet.py:112-133; conv feature encoder frozen as in
+ * src/config/train_triplet.yaml `freeze_convnet: True`) ---------------------------------------------------------------
+ * wav: 3B x N fp32 device rows: B anchors, then B positives, then B negatives (the zero-padded batches of the
+ * reference's collate_fn).  Computes the embeddings of all three, loss = nn.TripletMarginLoss(margin)(A, P, N) and the
+ * gradient of the loss wrt EVERY trainable parameter: LayerNorm(512), feature projection, positional conv (as the
+ * gradient of the weight-norm-folded weight), encoder LayerNorm, the 12 transformer layers (q/k/v fused, q rows carrying
+ * the head_dim^-0.5 scale) and the embedding head.  Activation gradients run the loss path's dgrad chain; every weight
+ * gradient dW = dY^T X is a tensor-core GEMM over the token dimension.  grads: nomad_b200_triplet_grad_floats() fp32
+ * values laid out as nomad_b200_triplet_grad_segment enumerates, all multiplied by *grad_scale_out (a power of two
+ * that keeps 16-bit activation gradients in range; divide it out).  The optimiser step itself (Adam, train_triplet.py:
+ * 92-107) is host plumbing: see nomad_b200/triplet.py. */
+NOMAD_B200_API int64_t nomad_b200_triplet_grad_floats(void);
+NOMAD_B200_API int nomad_b200_triplet_grad_segment(int i, char* name, int name_cap, int64_t* offset, int64_t* numel);
+NOMAD_B200_API size_t nomad_b200_triplet_workspace_bytes(int B, int64_t N);
+NOMAD_B200_API int nomad_b200_triplet_fwd_bwd(nomad_b200_handle* h, const float* wav_dev, int B, int64_t N, float margin,
+                               float* loss_dev, float* grads_dev, float* grad_scale_out, void* workspace_dev,
+                               size_t workspace_bytes, void* stream);
+
 /* ---- building block exposed for the parity tests --------------------------------------------------
  * C (m x n, ldc) = epilogue(A (m x k op_t, row stride lda elements, may overlap) * B^T (n x k op_t)).
  * flags: 1 bias, 2 GELU(erf), 4 + residual fp32 (ld = ldc), 8 store fp32 (c_f32), 16 store op_t (c_f16).

@@ -60,7 +60,7 @@ int make_plan(const int64_t* off, int B, Plan* p) {
     return 0;
 }
 
-size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
+size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save, bool train) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
         size_t at = o;
@@ -70,6 +70,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
     Workspace w;
     memset(&w, 0, sizeof(w));
     w.save = save;
+    w.train = train;
     const size_t F = (size_t)p.frames;
     w.meta = (UttMeta*)take(sizeof(UttMeta) * p.B);
     w.attn_items = (uint32_t*)take(sizeof(uint32_t) * p.attn_items.size());
@@ -105,7 +106,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
         op_t* qkv = (op_t*)take(2ull * 3 * EMBED * F);
         op_t* attn = (op_t*)take(2ull * EMBED * F);
         w.x0 = pre;
-        for (int l = 0; l < LAYERS; ++l) w.layer[l] = LayerBufs{qkv, attn, nullptr, pre, nullptr, pre};
+        for (int l = 0; l < LAYERS; ++l) w.layer[l] = LayerBufs{qkv, attn, nullptr, pre, nullptr, pre, nullptr};
     } else {
         w.x0 = (float*)take(4ull * EMBED * F);
         for (int l = 0; l < LAYERS; ++l) {
@@ -116,6 +117,7 @@ size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save) {
             L.pre1 = (float*)take(4ull * EMBED * F);
             L.ffn_aux = (op_t*)take(2ull * FFN * F);
             L.pre2 = (float*)take(4ull * EMBED * F);
+            L.ffn_h = train ? (op_t*)take(2ull * FFN * F) : nullptr;
         }
     }
     w.bytes = o;
@@ -638,7 +640,7 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
         {
             GemmOperand A{ws.xh, F, EMBED, 0, 0};
             GemmOperand Bw{fold_ln ? L.w_fc1_f : L.w_fc1, FFN, EMBED, 0, 0};
-            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, L.b_fc1, nullptr, nullptr, ws.ffn_h, FFN);
+            GemmEpilogue e = epi_linear(EPI_BIAS | EPI_GELU | EPI_OUT_H16, L.b_fc1, nullptr, nullptr, Lb.ffn_h ? Lb.ffn_h : ws.ffn_h, FFN);
             if (fold_ln) {
                 e.flags = EPI_LN_FOLD | EPI_GELU | EPI_OUT_H16;
                 e.ln_part = part1;
@@ -652,7 +654,7 @@ int forward_encoder(Handle* h, const Plan& p, const Workspace& ws, const float* 
             NB_TRY(gemm_h16(st, A, Bw, (int)F, FFN, EMBED, 1, e, impl));
         }
         {
-            GemmOperand A{ws.ffn_h, F, FFN, 0, 0};
+            GemmOperand A{Lb.ffn_h ? Lb.ffn_h : ws.ffn_h, F, FFN, 0, 0};
             GemmOperand Bw{L.w_fc2, EMBED, FFN, 0, 0};
             GemmEpilogue e = epi_linear(EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32, L.b_fc2, Lb.pre1, Lb.pre2, nullptr, EMBED);
             e.ln_stats = st1;

@@ -563,6 +563,543 @@ size_t nomad_b200_loss_workspace_bytes(int B, int64_t N, int with_grad) {
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------------------------
+// Backward of the encoder for the first B utterances of the batch (frames [0, Fe)): gradient wrt every layer input down
+// to the waveform (dgrad chain).  `seed_layer`: L1 seed of every layer output against the second half of the batch (the
+// loss path; 0 = none); L.g_pool: per-utterance gradient of the mean-pooled top layer.  `tc` (triplet fine-tuning,
+// triplet section below): also produce the parameter gradients of everything after the (frozen) conv feature encoder and
+// stop there.
+struct TrainCtx;
+static int train_hook_layer(Handle* h, const Workspace& ws, const LossBufs& L, TrainCtx* tc, int l, int stage, int B,
+                            long long Fe, const float* g_running, cudaStream_t st);
+static int train_hook_front(Handle* h, const Workspace& ws, const LossBufs& L, TrainCtx* tc, int stage, int B, long long Fe,
+                            long long pos_rows_e, cudaStream_t st);
+
+static int backward_chain(Handle* h, const Workspace& ws, const LossBufs& L, int B, long long Fe, long long R0e,
+                          long long pos_rows_e, int T, float seed_layer, float feature_grad_mult, float S,
+                          const float* est_dev, int64_t N, float* d_est_dev, cudaStream_t st, TrainCtx* tc) {
+    const Weights& w = h->w;
+    const int impl = h->gemm_impl;
+    const unsigned row_blocks = (unsigned)((Fe + 7) / 8);
+    auto epi_grad = [&](int flags, const float* resid, float* out_f, op_t* out_h, const op_t* aux, long long ld) {
+        GemmEpilogue e = epi_linear(flags, nullptr, resid, out_f, out_h, ld);
+        e.aux = aux;
+        return e;
+    };
+    NB_CUDA(cudaMemsetAsync(L.g_qkv, 0, 2ull * 3 * EMBED * Fe, st));
+    const float* g_running = nullptr;  // gradient wrt the current layer's output from the layers above
+    for (int l = LAYERS - 1; l >= 0; --l) {
+        const LayerWeights& W = w.layer[l];
+        const LayerBufs& Lb = ws.layer[l];
+        // final_layer_norm backward (+ L1 seed of this layer's output, + pooled-head gradient on the top layer)
+        ln768_bwd_kernel<<<row_blocks, 256, 0, st>>>(g_running, Lb.pre2, ws.meta, B, Fe, W.ln2_g, seed_layer,
+                                                     l == LAYERS - 1 ? L.g_pool : nullptr, L.g_b, L.g_bh);
+        NB_LAUNCHED();
+        if (tc) NB_TRY(train_hook_layer(h, ws, L, tc, l, 0, B, Fe, g_running, st));  // LN2 params, fc2 weight + bias
+        {   // fc2 dgrad, times gelu'(fc1 pre-activation)
+            GemmOperand A{L.g_bh, Fe, EMBED, 0, 0};
+            GemmOperand Bw{W.wt_fc2, FFN, EMBED, 0, 0};
+            GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, L.g_h, Lb.ffn_aux, FFN);
+            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, FFN, EMBED, 1, e, impl));
+        }
+        {   // fc1 dgrad + residual branch
+            GemmOperand A{L.g_h, Fe, FFN, 0, 0};
+            GemmOperand Bw{W.wt_fc1, EMBED, FFN, 0, 0};
+            GemmEpilogue e = epi_grad(EPI_RESID | EPI_OUT_F32, L.g_b, L.g_c, nullptr, nullptr, EMBED);
+            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, FFN, 1, e, impl));
+        }
+        if (tc) NB_TRY(train_hook_layer(h, ws, L, tc, l, 1, B, Fe, g_running, st));  // fc1 weight + bias (L.g_h is ready)
+        // self_attn_layer_norm backward
+        ln768_bwd_kernel<<<row_blocks, 256, 0, st>>>(L.g_c, Lb.pre1, ws.meta, B, Fe, W.ln1_g, 0.f, nullptr, L.g_b, L.g_bh);
+        NB_LAUNCHED();
+        if (tc) NB_TRY(train_hook_layer(h, ws, L, tc, l, 2, B, Fe, g_running, st));  // LN1 params, out_proj weight + bias
+        {   // out_proj dgrad
+            GemmOperand A{L.g_bh, Fe, EMBED, 0, 0};
+            GemmOperand Bw{W.wt_o, EMBED, EMBED, 0, 0};
+            GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.g_attn, nullptr, EMBED);
+            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, EMBED, 1, e, impl));
+        }
+        NB_TRY(launch_attention_bwd(st, Lb.qkv, Lb.attn, L.g_attn, Lb.lse, L.D, ws.meta, B, T, Fe, L.g_qkv));
+        if (tc) NB_TRY(train_hook_layer(h, ws, L, tc, l, 3, B, Fe, g_running, st));  // fused q/k/v weight + bias
+        {   // fused q/k/v dgrad + residual branch -> gradient wrt this layer's input
+            GemmOperand A{L.g_qkv, Fe, 3 * EMBED, 0, 0};
+            GemmOperand Bw{W.wt_qkv, EMBED, 3 * EMBED, 0, 0};
+            GemmEpilogue e = epi_grad(EPI_RESID | EPI_OUT_F32, L.g_b, L.g_a, nullptr, nullptr, EMBED);
+            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, 3 * EMBED, 1, e, impl));
+        }
+        g_running = L.g_a;
+    }
+    // encoder LayerNorm + positional conv backward
+    {
+        const long long rows_alloc = pos_rows_e + POS_K;
+        NB_CUDA(cudaMemsetAsync(L.pos_g, 0, 2ull * POS_G * POS_GC * rows_alloc, st));
+        if (tc) NB_TRY(train_hook_front(h, ws, L, tc, 0, B, Fe, pos_rows_e, st));  // encoder LayerNorm params (reads L.g_a)
+        pos_bwd_prep_kernel<<<row_blocks, 256, 0, st>>>(L.g_a, ws.x0, ws.pos_y, ws.pos_aux, ws.meta, B, Fe, w.lne_g,
+                                                        rows_alloc, L.g_b, L.pos_g);
+        NB_LAUNCHED();
+        if (tc) NB_TRY(train_hook_front(h, ws, L, tc, 1, B, Fe, pos_rows_e, st));  // positional conv weight + bias
+        if (impl == 0) {
+            NB_TRY(launch_posconv(st, L.pos_g, rows_alloc, pos_rows_e, w.pos_wt, nullptr, 0, L.pos_dy, nullptr));
+        } else {
+            GemmOperand A{L.pos_g, pos_rows_e, POS_GC, rows_alloc * POS_GC, 0};
+            GemmOperand Bw{w.pos_wt, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
+            GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.pos_dy, nullptr, EMBED);
+            e.out_bstride = POS_GC;
+            NB_TRY(gemm_h16(st, A, Bw, (int)pos_rows_e, POS_GC, POS_K * POS_GC, POS_G, e, impl));
+        }
+        pos_bwd_finish_kernel<<<row_blocks, 256, 0, st>>>(L.g_b, L.pos_dy, ws.meta, B, Fe, L.g_x0h);
+        NB_LAUNCHED();
+        if (tc) NB_TRY(train_hook_front(h, ws, L, tc, 2, B, Fe, pos_rows_e, st));  // projection weight + bias
+    }
+    {   // feature projection dgrad
+        GemmOperand A{L.g_x0h, Fe, EMBED, 0, 0};
+        GemmOperand Bw{w.proj_wt, CONV_DIM, EMBED, 0, 0};
+        GemmEpilogue e = epi_grad(EPI_OUT_F32, nullptr, L.g_ln0, nullptr, nullptr, CONV_DIM);
+        NB_TRY(gemm_h16(st, A, Bw, (int)Fe, CONV_DIM, EMBED, 1, e, impl));
+    }
+    if (tc) return train_hook_front(h, ws, L, tc, 3, B, Fe, pos_rows_e, st);  // LayerNorm(512) params; conv encoder frozen
+    // conv stack backward.  Gradient buffers start 8 rows into their allocation so that "row -1" reads zeros.
+    NB_CUDA(cudaMemsetAsync(L.gu_a, 0, 2ull * CONV_DIM * 8, st));
+    NB_CUDA(cudaMemsetAsync(L.gu_b, 0, 2ull * CONV_DIM * 8, st));
+    op_t* gu[7];
+    for (int l = 0; l < 7; ++l) gu[l] = ((l & 1) ? L.gu_b : L.gu_a) + 8 * CONV_DIM;
+    ln512_bwd_kernel<<<row_blocks, 256, 0, st>>>(L.g_ln0, ws.y[6], ws.aux[6], Fe, w.ln0_g, feature_grad_mult, gu[6]);
+    NB_LAUNCHED();
+    for (int l = 6; l >= 1; --l) {
+        const long long M = R0e >> l;  // rows at level l (estimate half)
+        if (CONV_KERNEL[l] == 2) {
+            // rows 2m and 2m+1 of level l-1 in one GEMM: N = 1024 = (tap, cin)
+            GemmOperand A{gu[l], M, CONV_DIM, 0, 0};
+            GemmOperand Bw{w.conv_wt[l], 2 * CONV_DIM, CONV_DIM, 0, 0};
+            GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1], ws.aux[l - 1], 2 * CONV_DIM);
+            NB_TRY(gemm_h16(st, A, Bw, (int)M, 2 * CONV_DIM, CONV_DIM, 1, e, impl));
+        } else {
+            {   // even rows 2m: taps 2 (from row m-1) and 0 (row m): overlapping rows starting one row early
+                GemmOperand A{gu[l] - CONV_DIM, M, CONV_DIM, 0, 0};
+                GemmOperand Bw{w.conv_wte[l], CONV_DIM, 2 * CONV_DIM, 0, 0};
+                GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1], ws.aux[l - 1], 2 * CONV_DIM);
+                NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, 2 * CONV_DIM, 1, e, impl));
+            }
+            {   // odd rows 2m+1: tap 1
+                GemmOperand A{gu[l], M, CONV_DIM, 0, 0};
+                GemmOperand Bw{w.conv_wt[l] + (size_t)CONV_DIM * CONV_DIM, CONV_DIM, CONV_DIM, 0, 0};
+                GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1] + CONV_DIM,
+                                          ws.aux[l - 1] + CONV_DIM, 2 * CONV_DIM);
+                NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, CONV_DIM, 1, e, impl));
+            }
+        }
+    }
+    // conv0 + GroupNorm backward: gu[0] = G0
+    NB_CUDA(cudaMemsetAsync(L.c0_sums, 0, 8ull * 2 * CONV_DIM * B, st));
+    conv0_bwd_stats_kernel<<<(unsigned)(R0e / 64), 256, 0, st>>>(gu[0], est_dev, ws.meta, B, w.conv0_w, ws.gn_stat, L.c0_sums);
+    NB_LAUNCHED();
+    conv0_bwd_consts_kernel<<<B, 128, 0, st>>>(L.c0_sums, ws.meta, w.conv0_w, ws.gn_stat, L.c0_consts);
+    NB_LAUNCHED();
+    {
+        GemmOperand A{gu[0], R0e, CONV_DIM, 0, 0};
+        GemmOperand Bw{w.conv0_wh, 16, CONV_DIM, 0, 0};
+        GemmEpilogue e = epi_grad(EPI_OUT_F32, nullptr, L.c0_V, nullptr, nullptr, 16);
+        NB_TRY(gemm_h16(st, A, Bw, (int)R0e, 16, CONV_DIM, 1, e, impl));
+    }
+    dim3 fgrid((unsigned)((N + 255) / 256), B);
+    conv0_bwd_finish_kernel<<<fgrid, 256, 0, st>>>(L.c0_V, est_dev, ws.meta, L.c0_consts, N, 1.0f / S, d_est_dev);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// =============================================================================================================
+// Triplet fine-tuning step (reference src/training/train_triplet.py:112-133, conv feature encoder frozen as in
+// src/config/train_triplet.yaml `freeze_convnet: True`): embeddings of anchors / positives / negatives ->
+// TripletMarginLoss(margin, p = 2, eps = 1e-6) -> gradients of EVERY trainable parameter (LayerNorm(512), feature
+// projection, positional conv, encoder LayerNorm, the 12 transformer layers, the embedding head).  The activation
+// gradients are the dgrad chain above; each weight gradient dW = dY^T X is a tensor-core GEMM over the token dimension
+// (both operands transposed into K-major first: two bandwidth-trivial passes), bias / LayerNorm gradients are column
+// reductions.  All gradients carry the power-of-two scale S of the chain; the caller divides it out.
+
+// flat gradient buffer (fp32): per layer [qkv_w 2304x768 | qkv_b | o_w | o_b | fc1_w | fc1_b | fc2_w | fc2_b | ln1_g | ln1_b |
+// ln2_g | ln2_b], then [enc_ln_g | enc_ln_b | pos_w 16x48x6144 (folded weight, layout [g][n][tap*48+c]) | pos_b |
+// proj_w 768x512 | proj_b | ln0_g | ln0_b | head_w 256x768 | head_b]
+struct TrainLayout {
+    static constexpr long long QKV_W = 0, QKV_B = QKV_W + 2304LL * 768, O_W = QKV_B + 2304, O_B = O_W + 768LL * 768,
+                               FC1_W = O_B + 768, FC1_B = FC1_W + 3072LL * 768, FC2_W = FC1_B + 3072,
+                               FC2_B = FC2_W + 768LL * 3072, LN1_G = FC2_B + 768, LN1_B = LN1_G + 768, LN2_G = LN1_B + 768,
+                               LN2_B = LN2_G + 768, LAYER = LN2_B + 768;
+    static constexpr long long ENC_G = LAYER * LAYERS, ENC_B = ENC_G + 768, POS_W = ENC_B + 768,
+                               POS_B = POS_W + (long long)POS_G * POS_GC * POS_K * POS_GC, PROJ_W = POS_B + 768,
+                               PROJ_B = PROJ_W + 768LL * 512, LN0_G = PROJ_B + 768, LN0_B = LN0_G + 512, HEAD_W = LN0_B + 512,
+                               HEAD_B = HEAD_W + 256LL * 768, TOTAL = HEAD_B + 256;
+};
+
+struct TrainCtx {
+    float* grads;     // TrainLayout::TOTAL floats, zeroed
+    op_t* tA;         // 3072 x Fp: transposed dY
+    op_t* tB;         // 3072 x Fp: transposed X
+    op_t* xh_tmp;     // F x 768: recomputed LayerNorm output (GEMM input of the layer being differentiated)
+    float* x_tmp;     // F x 768 fp32 scratch for the recomputation kernels
+    float* gy;        // [3B][256] gradient wrt the un-normalised head output
+    long long Fp;     // tokens rounded up to 8 (K of the weight-gradient GEMMs)
+};
+
+// in [rows][cols] (16-bit) -> out [cols][rows_p], columns rows..rows_p-1 zero
+__global__ void __launch_bounds__(256) transpose_h16_kernel(const op_t* __restrict__ in, long long rows, int cols,
+                                                            long long rows_p, op_t* __restrict__ out) {
+    __shared__ op_t tile[64][66];
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        tile[r][c] = (r0 + r < rows && c0 + c < cols) ? in[(r0 + r) * cols + c0 + c] : f2op(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, r = i & 63;
+        if (c0 + c < cols && r0 + r < rows_p) out[(long long)(c0 + c) * rows_p + r0 + r] = tile[r][c];
+    }
+}
+static int launch_transpose(cudaStream_t st, const op_t* in, long long rows, int cols, long long rows_p, op_t* out) {
+    dim3 grid((unsigned)((rows_p + 63) / 64), (unsigned)((cols + 63) / 64));
+    transpose_h16_kernel<<<grid, 256, 0, st>>>(in, rows, cols, rows_p, out);
+    NB_LAUNCHED();
+    return 0;
+}
+// dW[No][Ki] (fp32) = sum_t dY[t][no] X[t][ki]
+static int wgrad(cudaStream_t st, TrainCtx* tc, const op_t* dY, int No, const op_t* X, int Ki, long long F, float* dW) {
+    NB_TRY(launch_transpose(st, dY, F, No, tc->Fp, tc->tA));
+    NB_TRY(launch_transpose(st, X, F, Ki, tc->Fp, tc->tB));
+    GemmOperand A{tc->tA, No, tc->Fp, 0, 0};
+    GemmOperand Bw{tc->tB, Ki, tc->Fp, 0, 0};
+    GemmEpilogue e = epi_linear(EPI_OUT_F32, nullptr, nullptr, dW, nullptr, Ki);
+    return gemm_h16(st, A, Bw, No, Ki, (int)tc->Fp, 1, e, 0);
+}
+// out[c] += sum over rows of in[r][c]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, long long rows, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int g = threadIdx.x >> 6;
+    float s = 0.f;
+    if (c < cols)
+        for (long long r = (long long)blockIdx.y * 4 + g; r < rows; r += 4LL * gridDim.y) s += (float)in[r * cols + c];
+    __shared__ float red[4][64];
+    red[g][threadIdx.x & 63] = s;
+    __syncthreads();
+    if (g == 0 && c < cols) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+template <typename T>
+static int launch_colsum(cudaStream_t st, const T* in, long long rows, int cols, float* out) {
+    dim3 grid((unsigned)((cols + 63) / 64), 32);
+    colsum_kernel<T><<<grid, 256, 0, st>>>(in, rows, cols, out);
+    NB_LAUNCHED();
+    return 0;
+}
+// LayerNorm(768) parameter gradients: with g = gradient wrt the LayerNorm OUTPUT (g_in rows + g_pool[utt] broadcast, either
+// may be null) and xhat the normalised input: d_gamma += g * xhat, d_beta += g.  `pos_y` non-null: the input row is
+// x[f] + pos_y[pos row of f] (the encoder LayerNorm).
+__global__ void __launch_bounds__(256) ln768_param_grad_kernel(const float* __restrict__ g_in, const float* __restrict__ g_pool,
+                                                               const float* __restrict__ pre, const op_t* __restrict__ pos_y,
+                                                               const UttMeta* __restrict__ meta, int B, long long frames,
+                                                               float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    __shared__ float sg[EMBED], sb[EMBED];
+    for (int i = threadIdx.x; i < EMBED; i += 256) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    float ag[24], ab[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); f < frames; f += 8LL * gridDim.x) {
+        const int b = find_utt_by_frame(meta, B, (int)f);
+        const int t = (int)f - meta[b].frame0;
+        if (t >= meta[b].T) continue;
+        Row768f x, g;
+        load_row768(x, pre + f * EMBED, lane);
+        if (pos_y != nullptr) {
+            const long long m = (long long)meta[b].pos0 + t - POS_K / 2;
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const uint4 y = __ldg(reinterpret_cast<const uint4*>(pos_y + m * EMBED + (lane + 32 * h) * 8));
+                const float2 t0 = unpack_op(y.x), t1 = unpack_op(y.y), t2 = unpack_op(y.z), t3 = unpack_op(y.w);
+                float* v = x.v + 8 * h;
+                v[0] += t0.x; v[1] += t0.y; v[2] += t1.x; v[3] += t1.y; v[4] += t2.x; v[5] += t2.y; v[6] += t3.x; v[7] += t3.y;
+            }
+        }
+        normalise768(x);
+        if (g_in != nullptr) {
+            load_row768(g, g_in + f * EMBED, lane);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 24; ++i) g.v[i] = 0.f;
+        }
+        if (g_pool != nullptr) {
+            Row768f gp;
+            load_vec768(gp, g_pool + (long long)b * EMBED, lane);
+#pragma unroll
+            for (int i = 0; i < 24; ++i) g.v[i] += gp.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 24; ++i) { ag[i] = fmaf(g.v[i], x.v[i], ag[i]); ab[i] += g.v[i]; }
+    }
+#pragma unroll
+    for (int h = 0; h < 3; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&sg[(lane + 32 * h) * 8 + i], ag[8 * h + i]);
+            atomicAdd(&sb[(lane + 32 * h) * 8 + i], ab[8 * h + i]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < EMBED; i += 256) { atomicAdd(d_gamma + i, sg[i]); atomicAdd(d_beta + i, sb[i]); }
+}
+static int launch_ln768_param_grad(cudaStream_t st, const float* g_in, const float* g_pool, const float* pre, const op_t* pos_y,
+                                   const UttMeta* meta, int B, long long frames, float* dg, float* db) {
+    const unsigned blocks = (unsigned)std::min<long long>((frames + 7) / 8, 296);
+    ln768_param_grad_kernel<<<blocks, 256, 0, st>>>(g_in, g_pool, pre, pos_y, meta, B, frames, dg, db);
+    NB_LAUNCHED();
+    return 0;
+}
+// LayerNorm(512) parameter gradients from g (fp32, wrt the LayerNorm output) and the conv features y6 (16-bit)
+__global__ void __launch_bounds__(256) ln512_param_grad_kernel(const float* __restrict__ g, const op_t* __restrict__ y6,
+                                                               const UttMeta* __restrict__ meta, int B, long long rows,
+                                                               float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    __shared__ float sg[CONV_DIM], sb[CONV_DIM];
+    for (int i = threadIdx.x; i < CONV_DIM; i += 256) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    float ag[16], ab[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += 8LL * gridDim.x) {
+        const int b = find_utt_by_frame(meta, B, (int)row);
+        if ((int)row - meta[b].frame0 >= meta[b].T) continue;
+        float x[16], gg[16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c0 = (lane + 32 * h) * 8;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(y6 + row * CONV_DIM + c0));
+            float2 f;
+            f = unpack_op(u.x); x[8 * h + 0] = f.x; x[8 * h + 1] = f.y;
+            f = unpack_op(u.y); x[8 * h + 2] = f.x; x[8 * h + 3] = f.y;
+            f = unpack_op(u.z); x[8 * h + 4] = f.x; x[8 * h + 5] = f.y;
+            f = unpack_op(u.w); x[8 * h + 6] = f.x; x[8 * h + 7] = f.y;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + row * CONV_DIM + c0));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + row * CONV_DIM + c0 + 4));
+            gg[8 * h + 0] = g0.x; gg[8 * h + 1] = g0.y; gg[8 * h + 2] = g0.z; gg[8 * h + 3] = g0.w;
+            gg[8 * h + 4] = g1.x; gg[8 * h + 5] = g1.y; gg[8 * h + 6] = g1.z; gg[8 * h + 7] = g1.w;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += x[i];
+        const float mean = warp_sum(s) * (1.0f / CONV_DIM);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { x[i] -= mean; q = fmaf(x[i], x[i], q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / CONV_DIM) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { ag[i] = fmaf(gg[i], x[i] * rstd, ag[i]); ab[i] += gg[i]; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&sg[(lane + 32 * h) * 8 + i], ag[8 * h + i]);
+            atomicAdd(&sb[(lane + 32 * h) * 8 + i], ab[8 * h + i]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CONV_DIM; i += 256) { atomicAdd(d_gamma + i, sg[i]); atomicAdd(d_beta + i, sb[i]); }
+}
+// Positional-conv weight gradient: dW[g][n][tap][c] = sum_p dY[g][p][n] X[g][p - 64 + tap][c] over the zero-padded
+// grouped layouts (dY = the scattered g_z * gelu' rows of pos_bwd_prep_kernel, X = the forward's scattered input).
+// One block per (group, tap); thread (n, c-octet) owns 8 outputs; rows staged through shared memory 64 at a time.
+__global__ void __launch_bounds__(288) pos_wgrad_kernel(const op_t* __restrict__ dy, const op_t* __restrict__ x,
+                                                        long long rows_alloc, long long pos_rows, float* __restrict__ dw) {
+    const int g = blockIdx.y, tap = blockIdx.x;
+    const int n = threadIdx.x / 6, c0 = (threadIdx.x % 6) * 8;
+    __shared__ float sdy[64][POS_GC], sx[64][POS_GC];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const op_t* dyg = dy + (long long)g * rows_alloc * POS_GC;
+    const op_t* xg = x + (long long)g * rows_alloc * POS_GC;
+    for (long long p0 = POS_K / 2; p0 < pos_rows + POS_K / 2; p0 += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * POS_GC; i += 288) {
+            const int r = i / POS_GC, c = i % POS_GC;
+            const long long p = p0 + r, q = p - POS_K / 2 + tap;
+            sdy[r][c] = p < rows_alloc ? op2f(dyg[p * POS_GC + c]) : 0.f;
+            sx[r][c] = q < rows_alloc ? op2f(xg[q * POS_GC + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 64; ++r) {
+            const float d = sdy[r][n];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(d, sx[r][c0 + i], acc[i]);
+        }
+    }
+    float* o = dw + ((long long)(g * POS_GC + n)) * (POS_K * POS_GC) + (long long)tap * POS_GC + c0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
+}
+// column sums of the grouped layout: bias[g * 48 + n] = sum_p dY[g][p][n]
+__global__ void __launch_bounds__(256) pos_bias_grad_kernel(const op_t* __restrict__ dy, long long rows_alloc, float* __restrict__ db) {
+    const int g = blockIdx.x;
+    const int n = threadIdx.x % POS_GC, part = threadIdx.x / POS_GC;  // 5 row partitions (240 threads active)
+    __shared__ float red[5][POS_GC];
+    if (part < 5) {
+        float s = 0.f;
+        for (long long p = part; p < rows_alloc; p += 5) s += op2f(dy[((long long)g * rows_alloc + p) * POS_GC + n]);
+        red[part][n] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < POS_GC) db[g * POS_GC + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x] + red[4][threadIdx.x];
+}
+
+// Triplet head: e = normalize(W relu(pooled) + b) for anchor / positive / negative i; loss_i = max(||e_a - e_p + eps|| -
+// ||e_a - e_n + eps|| + margin, 0) (torch.nn.TripletMarginLoss: pairwise_distance adds eps = 1e-6 to the difference);
+// gy[u][o] = S/B * d loss_i / d y_u[o] with y the un-normalised head output.  One block of 256 threads per triplet.
+__global__ void __launch_bounds__(256) triplet_head_kernel(const float* __restrict__ pooled, int B, const float* __restrict__ head_wt,
+                                                           const float* __restrict__ head_b, float margin, float scale,
+                                                           double* __restrict__ loss_acc, float* __restrict__ gy) {
+    const int i = blockIdx.x, tid = threadIdx.x;
+    __shared__ float pl[3][EMBED];
+    __shared__ float red[4][8];
+    for (int k = tid; k < EMBED; k += 256)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) pl[u][k] = fmaxf(pooled[((long long)u * B + i) * EMBED + k], 0.f);
+    __syncthreads();
+    float y[3] = {head_b[tid], head_b[tid], head_b[tid]};
+    for (int k = 0; k < EMBED; ++k) {
+        const float w = __ldg(head_wt + k * EMB + tid);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) y[u] = fmaf(pl[u][k], w, y[u]);
+    }
+    auto block_sum = [&](float v, int slot) {
+        v = warp_sum(v);
+        __syncthreads();
+        if ((tid & 31) == 0) red[slot][tid >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[slot][w];
+        return t;
+    };
+    float nrm[3], e[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        nrm[u] = fmaxf(sqrtf(block_sum(y[u] * y[u], u)), 1e-12f);
+        e[u] = y[u] / nrm[u];
+    }
+    const float dp = e[0] - e[1] + 1e-6f, dn = e[0] - e[2] + 1e-6f;
+    const float d_ap = sqrtf(block_sum(dp * dp, 0)), d_an = sqrtf(block_sum(dn * dn, 1));
+    const float li = d_ap - d_an + margin;
+    if (tid == 0 && li > 0.f) atomicAdd(loss_acc, (double)li);
+    float ge[3] = {0.f, 0.f, 0.f};
+    if (li > 0.f) {
+        const float a = dp / fmaxf(d_ap, 1e-20f), c = dn / fmaxf(d_an, 1e-20f);
+        ge[0] = scale * (a - c);
+        ge[1] = -scale * a;
+        ge[2] = scale * c;
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const float dot = block_sum(ge[u] * e[u], 2);
+        gy[((long long)u * B + i) * EMB + tid] = (ge[u] - e[u] * dot) / nrm[u];  // backward of y / max(||y||, eps)
+    }
+}
+// head parameter gradients and the pooled-feature gradient from gy
+__global__ void __launch_bounds__(256) head_param_grad_kernel(const float* __restrict__ gy, const float* __restrict__ pooled, int n_utt,
+                                                              float* __restrict__ dW, float* __restrict__ db) {
+    const int o = blockIdx.x;  // output row of the head
+    float bsum = 0.f;
+    for (int k = threadIdx.x; k < EMBED; k += 256) {
+        float a = 0.f;
+        for (int u = 0; u < n_utt; ++u) a = fmaf(gy[(long long)u * EMB + o], fmaxf(pooled[(long long)u * EMBED + k], 0.f), a);
+        dW[(long long)o * EMBED + k] = a;
+    }
+    if (threadIdx.x == 0) {
+        for (int u = 0; u < n_utt; ++u) bsum += gy[(long long)u * EMB + o];
+        db[o] = bsum;
+    }
+}
+__global__ void __launch_bounds__(256) head_pool_grad_kernel(const float* __restrict__ gy, const float* __restrict__ pooled,
+                                                             const UttMeta* __restrict__ meta, const float* __restrict__ head_wt,
+                                                             float* __restrict__ g_pool) {
+    const int u = blockIdx.x;
+    __shared__ float g[EMB];
+    g[threadIdx.x] = gy[(long long)u * EMB + threadIdx.x];
+    __syncthreads();
+    const float invT = 1.0f / (float)meta[u].T;
+    for (int k = threadIdx.x; k < EMBED; k += 256) {
+        float a = 0.f;
+        for (int o = 0; o < EMB; ++o) a = fmaf(g[o], __ldg(head_wt + (long long)k * EMB + o), a);
+        g_pool[(long long)u * EMBED + k] = pooled[(long long)u * EMBED + k] > 0.f ? a * invT : 0.f;
+    }
+}
+__global__ void triplet_loss_finalize_kernel(const double* __restrict__ acc, double inv_b, float* __restrict__ loss) {
+    *loss = (float)(acc[0] * inv_b);
+}
+
+// ---- hooks called from backward_chain --------------------------------------------------------------------------
+static int train_hook_layer(Handle* h, const Workspace& ws, const LossBufs& L, TrainCtx* tc, int l, int stage, int B,
+                            long long Fe, const float* g_running, cudaStream_t st) {
+    const Weights& w = h->w;
+    const LayerWeights& W = w.layer[l];
+    const LayerBufs& Lb = ws.layer[l];
+    float* G = tc->grads + TrainLayout::LAYER * l;
+    if (stage == 0) {  // final_layer_norm params (incoming: g_running + pooled gradient on the top layer); fc2
+        NB_TRY(launch_ln768_param_grad(st, g_running, l == LAYERS - 1 ? L.g_pool : nullptr, Lb.pre2, nullptr, ws.meta, B, Fe,
+                                       G + TrainLayout::LN2_G, G + TrainLayout::LN2_B));
+        NB_TRY(wgrad(st, tc, L.g_bh, EMBED, Lb.ffn_h, FFN, Fe, G + TrainLayout::FC2_W));
+        NB_TRY(launch_colsum<float>(st, L.g_b, Fe, EMBED, G + TrainLayout::FC2_B));
+    } else if (stage == 1) {  // fc1: input = LayerNorm1(pre1), recomputed
+        NB_TRY(launch_ln768(st, Lb.pre1, ws.meta, B, Fe, W.ln1_g, W.ln1_b, nullptr, tc->xh_tmp, nullptr, nullptr, 0));
+        NB_TRY(wgrad(st, tc, L.g_h, FFN, tc->xh_tmp, EMBED, Fe, G + TrainLayout::FC1_W));
+        NB_TRY(launch_colsum<op_t>(st, L.g_h, Fe, FFN, G + TrainLayout::FC1_B));
+    } else if (stage == 2) {  // self_attn_layer_norm params (incoming L.g_c); out_proj
+        NB_TRY(launch_ln768_param_grad(st, L.g_c, nullptr, Lb.pre1, nullptr, ws.meta, B, Fe, G + TrainLayout::LN1_G,
+                                       G + TrainLayout::LN1_B));
+        NB_TRY(wgrad(st, tc, L.g_bh, EMBED, Lb.attn, EMBED, Fe, G + TrainLayout::O_W));
+        NB_TRY(launch_colsum<float>(st, L.g_b, Fe, EMBED, G + TrainLayout::O_B));
+    } else {  // fused q/k/v: input = this layer's input (previous final_layer_norm output / encoder LayerNorm output)
+        if (l > 0) {
+            NB_TRY(launch_ln768(st, ws.layer[l - 1].pre2, ws.meta, B, Fe, w.layer[l - 1].ln2_g, w.layer[l - 1].ln2_b, nullptr,
+                                tc->xh_tmp, nullptr, nullptr, 0));
+        } else {
+            NB_TRY(launch_pos_finish_ln(st, ws.x0, ws.pos_y, ws.meta, B, Fe, w.lne_g, w.lne_b, tc->x_tmp, tc->xh_tmp));
+        }
+        NB_TRY(wgrad(st, tc, L.g_qkv, 3 * EMBED, tc->xh_tmp, EMBED, Fe, G + TrainLayout::QKV_W));
+        NB_TRY(launch_colsum<op_t>(st, L.g_qkv, Fe, 3 * EMBED, G + TrainLayout::QKV_B));
+    }
+    return 0;
+}
+
+static int train_hook_front(Handle* h, const Workspace& ws, const LossBufs& L, TrainCtx* tc, int stage, int B, long long Fe,
+                            long long pos_rows_e, cudaStream_t st) {
+    const Weights& w = h->w;
+    float* G = tc->grads;
+    const long long rows_alloc = pos_rows_e + POS_K;
+    if (stage == 0) {  // encoder LayerNorm params: input x0 + pos_y, incoming gradient L.g_a
+        NB_TRY(launch_ln768_param_grad(st, L.g_a, nullptr, ws.x0, ws.pos_y, ws.meta, B, Fe, G + TrainLayout::ENC_G, G + TrainLayout::ENC_B));
+    } else if (stage == 1) {  // positional conv (folded weight) + bias: dY = L.pos_g, X = ws.pos_g
+        dim3 grid(POS_K, POS_G);
+        pos_wgrad_kernel<<<grid, 288, 0, st>>>(L.pos_g, ws.pos_g, rows_alloc, pos_rows_e, G + TrainLayout::POS_W);
+        NB_LAUNCHED();
+        pos_bias_grad_kernel<<<POS_G, 256, 0, st>>>(L.pos_g, rows_alloc, G + TrainLayout::POS_B);
+        NB_LAUNCHED();
+    } else if (stage == 2) {  // feature projection: dY = L.g_x0h, X = LayerNorm(512) output
+        NB_TRY(wgrad(st, tc, L.g_x0h, EMBED, ws.ln0_out, CONV_DIM, Fe, G + TrainLayout::PROJ_W));
+        NB_TRY(launch_colsum<op_t>(st, L.g_x0h, Fe, EMBED, G + TrainLayout::PROJ_B));
+    } else {  // LayerNorm(512) params: incoming L.g_ln0, input = conv features (level 6)
+        const unsigned blocks = (unsigned)std::min<long long>((Fe + 7) / 8, 296);
+        ln512_param_grad_kernel<<<blocks, 256, 0, st>>>(L.g_ln0, ws.y[6], ws.meta, B, Fe, G + TrainLayout::LN0_G, G + TrainLayout::LN0_B);
+        NB_LAUNCHED();
+    }
+    return 0;
+}
+
+static size_t train_extra_bytes(long long F, int n_utt) {
+    const long long Fp = (F + 7) / 8 * 8;
+    auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+    return al(2ull * FFN * Fp) * 2 + al(2ull * EMBED * F) + al(4ull * EMBED * F) + al(4ull * EMB * n_utt) + 4096;
+}
+
 // phase 0: the whole step; 1: only the per-call metadata upload (the part of a step that cannot live in a CUDA graph:
 // it goes through the handle's pinned staging ring); 2: the whole step except that upload (what the graph holds)
 static int loss_run(nomad_b200_handle* hh, const float* est_dev, const float* clean_dev, int B, int64_t N,
@@ -622,122 +1159,7 @@ static int loss_run(nomad_b200_handle* hh, const float* est_dev, const float* cl
     if (!with_grad) return 0;
 
     // ------------------------------------------------------------------ backward (estimate half)
-    auto epi_grad = [&](int flags, const float* resid, float* out_f, op_t* out_h, const op_t* aux, long long ld) {
-        GemmEpilogue e = epi_linear(flags, nullptr, resid, out_f, out_h, ld);
-        e.aux = aux;
-        return e;
-    };
-    NB_CUDA(cudaMemsetAsync(L.g_qkv, 0, 2ull * 3 * EMBED * Fe, st));
-    const float* g_running = nullptr;  // gradient wrt the current layer's output from the layers above
-    for (int l = LAYERS - 1; l >= 0; --l) {
-        const LayerWeights& W = w.layer[l];
-        const LayerBufs& Lb = ws.layer[l];
-        // final_layer_norm backward (+ L1 seed of this layer's output, + pooled-head gradient on the top layer)
-        ln768_bwd_kernel<<<row_blocks, 256, 0, st>>>(g_running, Lb.pre2, ws.meta, B, Fe, W.ln2_g, seed_layer,
-                                                     l == LAYERS - 1 ? L.g_pool : nullptr, L.g_b, L.g_bh);
-        NB_LAUNCHED();
-        {   // fc2 dgrad, times gelu'(fc1 pre-activation)
-            GemmOperand A{L.g_bh, Fe, EMBED, 0, 0};
-            GemmOperand Bw{W.wt_fc2, FFN, EMBED, 0, 0};
-            GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, L.g_h, Lb.ffn_aux, FFN);
-            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, FFN, EMBED, 1, e, impl));
-        }
-        {   // fc1 dgrad + residual branch
-            GemmOperand A{L.g_h, Fe, FFN, 0, 0};
-            GemmOperand Bw{W.wt_fc1, EMBED, FFN, 0, 0};
-            GemmEpilogue e = epi_grad(EPI_RESID | EPI_OUT_F32, L.g_b, L.g_c, nullptr, nullptr, EMBED);
-            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, FFN, 1, e, impl));
-        }
-        // self_attn_layer_norm backward
-        ln768_bwd_kernel<<<row_blocks, 256, 0, st>>>(L.g_c, Lb.pre1, ws.meta, B, Fe, W.ln1_g, 0.f, nullptr, L.g_b, L.g_bh);
-        NB_LAUNCHED();
-        {   // out_proj dgrad
-            GemmOperand A{L.g_bh, Fe, EMBED, 0, 0};
-            GemmOperand Bw{W.wt_o, EMBED, EMBED, 0, 0};
-            GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.g_attn, nullptr, EMBED);
-            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, EMBED, 1, e, impl));
-        }
-        NB_TRY(launch_attention_bwd(st, Lb.qkv, Lb.attn, L.g_attn, Lb.lse, L.D, ws.meta, B, T, Fe, L.g_qkv));
-        {   // fused q/k/v dgrad + residual branch -> gradient wrt this layer's input
-            GemmOperand A{L.g_qkv, Fe, 3 * EMBED, 0, 0};
-            GemmOperand Bw{W.wt_qkv, EMBED, 3 * EMBED, 0, 0};
-            GemmEpilogue e = epi_grad(EPI_RESID | EPI_OUT_F32, L.g_b, L.g_a, nullptr, nullptr, EMBED);
-            NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, 3 * EMBED, 1, e, impl));
-        }
-        g_running = L.g_a;
-    }
-    // encoder LayerNorm + positional conv backward
-    {
-        const long long rows_alloc = pos_rows_e + POS_K;
-        NB_CUDA(cudaMemsetAsync(L.pos_g, 0, 2ull * POS_G * POS_GC * rows_alloc, st));
-        pos_bwd_prep_kernel<<<row_blocks, 256, 0, st>>>(L.g_a, ws.x0, ws.pos_y, ws.pos_aux, ws.meta, B, Fe, w.lne_g,
-                                                        rows_alloc, L.g_b, L.pos_g);
-        NB_LAUNCHED();
-        if (impl == 0) {
-            NB_TRY(launch_posconv(st, L.pos_g, rows_alloc, pos_rows_e, w.pos_wt, nullptr, 0, L.pos_dy, nullptr));
-        } else {
-            GemmOperand A{L.pos_g, pos_rows_e, POS_GC, rows_alloc * POS_GC, 0};
-            GemmOperand Bw{w.pos_wt, POS_GC, (long long)POS_K * POS_GC, (long long)POS_GC * POS_K * POS_GC, 0};
-            GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.pos_dy, nullptr, EMBED);
-            e.out_bstride = POS_GC;
-            NB_TRY(gemm_h16(st, A, Bw, (int)pos_rows_e, POS_GC, POS_K * POS_GC, POS_G, e, impl));
-        }
-        pos_bwd_finish_kernel<<<row_blocks, 256, 0, st>>>(L.g_b, L.pos_dy, ws.meta, B, Fe, L.g_x0h);
-        NB_LAUNCHED();
-    }
-    {   // feature projection dgrad
-        GemmOperand A{L.g_x0h, Fe, EMBED, 0, 0};
-        GemmOperand Bw{w.proj_wt, CONV_DIM, EMBED, 0, 0};
-        GemmEpilogue e = epi_grad(EPI_OUT_F32, nullptr, L.g_ln0, nullptr, nullptr, CONV_DIM);
-        NB_TRY(gemm_h16(st, A, Bw, (int)Fe, CONV_DIM, EMBED, 1, e, impl));
-    }
-    // conv stack backward.  Gradient buffers start 8 rows into their allocation so that "row -1" reads zeros.
-    NB_CUDA(cudaMemsetAsync(L.gu_a, 0, 2ull * CONV_DIM * 8, st));
-    NB_CUDA(cudaMemsetAsync(L.gu_b, 0, 2ull * CONV_DIM * 8, st));
-    op_t* gu[7];
-    for (int l = 0; l < 7; ++l) gu[l] = ((l & 1) ? L.gu_b : L.gu_a) + 8 * CONV_DIM;
-    ln512_bwd_kernel<<<row_blocks, 256, 0, st>>>(L.g_ln0, ws.y[6], ws.aux[6], Fe, w.ln0_g, feature_grad_mult, gu[6]);
-    NB_LAUNCHED();
-    for (int l = 6; l >= 1; --l) {
-        const long long M = R0e >> l;  // rows at level l (estimate half)
-        if (CONV_KERNEL[l] == 2) {
-            // rows 2m and 2m+1 of level l-1 in one GEMM: N = 1024 = (tap, cin)
-            GemmOperand A{gu[l], M, CONV_DIM, 0, 0};
-            GemmOperand Bw{w.conv_wt[l], 2 * CONV_DIM, CONV_DIM, 0, 0};
-            GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1], ws.aux[l - 1], 2 * CONV_DIM);
-            NB_TRY(gemm_h16(st, A, Bw, (int)M, 2 * CONV_DIM, CONV_DIM, 1, e, impl));
-        } else {
-            {   // even rows 2m: taps 2 (from row m-1) and 0 (row m): overlapping rows starting one row early
-                GemmOperand A{gu[l] - CONV_DIM, M, CONV_DIM, 0, 0};
-                GemmOperand Bw{w.conv_wte[l], CONV_DIM, 2 * CONV_DIM, 0, 0};
-                GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1], ws.aux[l - 1], 2 * CONV_DIM);
-                NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, 2 * CONV_DIM, 1, e, impl));
-            }
-            {   // odd rows 2m+1: tap 1
-                GemmOperand A{gu[l], M, CONV_DIM, 0, 0};
-                GemmOperand Bw{w.conv_wt[l] + (size_t)CONV_DIM * CONV_DIM, CONV_DIM, CONV_DIM, 0, 0};
-                GemmEpilogue e = epi_grad(EPI_MUL_AUX | EPI_OUT_H16, nullptr, nullptr, gu[l - 1] + CONV_DIM,
-                                          ws.aux[l - 1] + CONV_DIM, 2 * CONV_DIM);
-                NB_TRY(gemm_h16(st, A, Bw, (int)M, CONV_DIM, CONV_DIM, 1, e, impl));
-            }
-        }
-    }
-    // conv0 + GroupNorm backward: gu[0] = G0
-    NB_CUDA(cudaMemsetAsync(L.c0_sums, 0, 8ull * 2 * CONV_DIM * B, st));
-    conv0_bwd_stats_kernel<<<(unsigned)(R0e / 64), 256, 0, st>>>(gu[0], est_dev, ws.meta, B, w.conv0_w, ws.gn_stat, L.c0_sums);
-    NB_LAUNCHED();
-    conv0_bwd_consts_kernel<<<B, 128, 0, st>>>(L.c0_sums, ws.meta, w.conv0_w, ws.gn_stat, L.c0_consts);
-    NB_LAUNCHED();
-    {
-        GemmOperand A{gu[0], R0e, CONV_DIM, 0, 0};
-        GemmOperand Bw{w.conv0_wh, 16, CONV_DIM, 0, 0};
-        GemmEpilogue e = epi_grad(EPI_OUT_F32, nullptr, L.c0_V, nullptr, nullptr, 16);
-        NB_TRY(gemm_h16(st, A, Bw, (int)R0e, 16, CONV_DIM, 1, e, impl));
-    }
-    dim3 fgrid((unsigned)((N + 255) / 256), B);
-    conv0_bwd_finish_kernel<<<fgrid, 256, 0, st>>>(L.c0_V, est_dev, ws.meta, L.c0_consts, N, 1.0f / S, d_est_dev);
-    NB_LAUNCHED();
-    return 0;
+    return backward_chain(h, ws, L, B, Fe, R0e, pos_rows_e, T, seed_layer, feature_grad_mult, S, est_dev, N, d_est_dev, st, nullptr);
 }
 
 extern "C" {
@@ -816,6 +1238,115 @@ int nomad_b200_loss_fwd_bwd(nomad_b200_handle* hh, const float* est_dev, const f
     NB_CUDA(cudaMemcpyAsync(loss_dev, s_loss, 4, cudaMemcpyDeviceToDevice, st));
     if (with_grad) NB_CUDA(cudaMemcpyAsync(d_est_dev, s_grad, bn * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+}  // extern "C"
+
+// ---- triplet fine-tuning step: C ABI ---------------------------------------------------------------------------
+extern "C" {
+
+int64_t nomad_b200_triplet_grad_floats(void) { return TrainLayout::TOTAL; }
+
+// segment i of the flat gradient buffer: name, offset and element count; returns 0 while i is valid, 1 past the end
+int nomad_b200_triplet_grad_segment(int i, char* name, int name_cap, int64_t* offset, int64_t* numel) {
+    static const struct { const char* n; long long off, cnt; } per_layer[12] = {
+        {"qkv.weight", TrainLayout::QKV_W, 2304LL * 768}, {"qkv.bias", TrainLayout::QKV_B, 2304},
+        {"self_attn.out_proj.weight", TrainLayout::O_W, 768LL * 768}, {"self_attn.out_proj.bias", TrainLayout::O_B, 768},
+        {"fc1.weight", TrainLayout::FC1_W, 3072LL * 768}, {"fc1.bias", TrainLayout::FC1_B, 3072},
+        {"fc2.weight", TrainLayout::FC2_W, 768LL * 3072}, {"fc2.bias", TrainLayout::FC2_B, 768},
+        {"self_attn_layer_norm.weight", TrainLayout::LN1_G, 768}, {"self_attn_layer_norm.bias", TrainLayout::LN1_B, 768},
+        {"final_layer_norm.weight", TrainLayout::LN2_G, 768}, {"final_layer_norm.bias", TrainLayout::LN2_B, 768}};
+    static const struct { const char* n; long long off, cnt; } global[10] = {
+        {"ssl_model.encoder.layer_norm.weight", TrainLayout::ENC_G, 768}, {"ssl_model.encoder.layer_norm.bias", TrainLayout::ENC_B, 768},
+        {"ssl_model.encoder.pos_conv.0.folded_weight", TrainLayout::POS_W, (long long)POS_G * POS_GC * POS_K * POS_GC},
+        {"ssl_model.encoder.pos_conv.0.bias", TrainLayout::POS_B, 768},
+        {"ssl_model.post_extract_proj.weight", TrainLayout::PROJ_W, 768LL * 512}, {"ssl_model.post_extract_proj.bias", TrainLayout::PROJ_B, 768},
+        {"ssl_model.layer_norm.weight", TrainLayout::LN0_G, 512}, {"ssl_model.layer_norm.bias", TrainLayout::LN0_B, 512},
+        {"embedding_layer.1.weight", TrainLayout::HEAD_W, 256LL * 768}, {"embedding_layer.1.bias", TrainLayout::HEAD_B, 256}};
+    if (i < 0 || name == nullptr || offset == nullptr || numel == nullptr) return 1;
+    if (i < 12 * LAYERS) {
+        const int l = i / 12, k = i % 12;
+        snprintf(name, name_cap, "ssl_model.encoder.layers.%d.%s", l, per_layer[k].n);
+        *offset = TrainLayout::LAYER * l + per_layer[k].off;
+        *numel = per_layer[k].cnt;
+        return 0;
+    }
+    i -= 12 * LAYERS;
+    if (i >= 10) return 1;
+    snprintf(name, name_cap, "%s", global[i].n);
+    *offset = global[i].off;
+    *numel = global[i].cnt;
+    return 0;
+}
+
+static int triplet_plan(int B, int64_t N, Plan* p) {
+    NB_CHECK(B > 0 && N >= NOMAD_B200_MIN_SAMPLES, "triplet: need B > 0 and N >= %d samples", NOMAD_B200_MIN_SAMPLES);
+    std::vector<int64_t> off(3 * (size_t)B + 1);
+    for (int b = 0; b <= 3 * B; ++b) off[b] = (int64_t)b * N;
+    return make_plan(off.data(), 3 * B, p);
+}
+
+size_t nomad_b200_triplet_workspace_bytes(int B, int64_t N) {
+    Plan p;
+    if (triplet_plan(B, N, &p)) return 0;
+    const size_t fwd = carve_workspace(p, nullptr, nullptr, true, true);
+    const long long pos_rows = p.frames + (long long)POS_GAP * 3 * B + POS_K / 2;
+    return fwd + carve_loss(p, 3 * B, p.frames, p.rows0, pos_rows, true, nullptr, nullptr) + train_extra_bytes(p.frames, 3 * B) + 4096;
+}
+
+// wav_dev: 3B x N fp32 (anchors, then positives, then negatives); loss_dev: 1 float; grads_dev:
+// nomad_b200_triplet_grad_floats() floats (zeroed here) = grad_scale_out[0] * d loss / d parameter.
+int nomad_b200_triplet_fwd_bwd(nomad_b200_handle* hh, const float* wav_dev, int B, int64_t N, float margin, float* loss_dev,
+                               float* grads_dev, float* grad_scale_out, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    NB_CHECK(hh != nullptr, "null nomad_b200 handle");
+    Handle* h = &hh->h;
+    NB_CHECK(wav_dev && loss_dev && grads_dev && grad_scale_out && workspace_dev, "triplet: null pointer");
+    NB_CHECK(h->gemm_impl == 0, "triplet: tensor-core GEMMs only");
+    NB_CHECK(((uintptr_t)workspace_dev & 1023) == 0, "triplet: workspace must be 1024-byte aligned");
+    NB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Weights& w = h->w;
+    Plan p;
+    NB_TRY(triplet_plan(B, N, &p));
+    const int U = 3 * B;
+    const long long F = p.frames, R0 = p.rows0;
+    const long long pos_rows = F + (long long)POS_GAP * U + POS_K / 2;
+    Workspace ws;
+    const size_t fwd_bytes = carve_workspace(p, workspace_dev, &ws, true, true);
+    LossBufs L;
+    const size_t loss_bytes = carve_loss(p, U, F, R0, pos_rows, true, (char*)workspace_dev + fwd_bytes, &L);
+    const size_t extra = train_extra_bytes(F, U);
+    NB_CHECK(workspace_bytes >= fwd_bytes + loss_bytes + extra, "triplet: workspace too small (%zu < %zu bytes)", workspace_bytes,
+             fwd_bytes + loss_bytes + extra);
+    TrainCtx tc;
+    {
+        auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+        char* q = (char*)workspace_dev + fwd_bytes + loss_bytes;
+        tc.Fp = (F + 7) / 8 * 8;
+        tc.tA = (op_t*)q; q += al(2ull * FFN * tc.Fp);
+        tc.tB = (op_t*)q; q += al(2ull * FFN * tc.Fp);
+        tc.xh_tmp = (op_t*)q; q += al(2ull * EMBED * F);
+        tc.x_tmp = (float*)q; q += al(4ull * EMBED * F);
+        tc.gy = (float*)q;
+        tc.grads = grads_dev;
+    }
+    NB_TRY(upload_meta(h, p, ws, st));
+    NB_CUDA(cudaMemsetAsync(grads_dev, 0, sizeof(float) * TrainLayout::TOTAL, st));
+    NB_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * 16, st));
+    NB_TRY(forward_encoder(h, p, ws, wav_dev, st, nullptr, 0));
+    NB_TRY(launch_pool_head(st, ws.x, ws.meta, U, w.head_wt, w.head_b, L.emb, L.pooled));
+    // gradient scale: power of two so that the 16-bit activation gradients sit in fp16's normal range
+    const float S = (float)std::exp2(std::ceil(std::log2((double)B * p.max_T)) + 10.0);
+    triplet_head_kernel<<<B, 256, 0, st>>>(L.pooled, B, w.head_wt, w.head_b, margin, S / (float)B, L.acc, tc.gy);
+    NB_LAUNCHED();
+    triplet_loss_finalize_kernel<<<1, 1, 0, st>>>(L.acc, 1.0 / (double)B, loss_dev);
+    NB_LAUNCHED();
+    head_param_grad_kernel<<<EMB, 256, 0, st>>>(tc.gy, L.pooled, U, grads_dev + TrainLayout::HEAD_W, grads_dev + TrainLayout::HEAD_B);
+    NB_LAUNCHED();
+    head_pool_grad_kernel<<<U, 256, 0, st>>>(tc.gy, L.pooled, ws.meta, w.head_wt, L.g_pool);
+    NB_LAUNCHED();
+    *grad_scale_out = S;
+    return backward_chain(h, ws, L, U, F, R0, pos_rows, p.max_T, 0.f, 1.0f, S, wav_dev, N, nullptr, st, &tc);
 }
 
 }  // extern "C"

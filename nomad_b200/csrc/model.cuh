@@ -111,10 +111,12 @@ struct LayerBufs {
     float* pre1;    // frames x 768: x_in + out_proj(attn)        (input of self_attn_layer_norm)
     op_t* ffn_aux;  // frames x 3072: gelu'(fc1 pre-activation)   (save mode) or nullptr
     float* pre2;    // frames x 768: x1 + fc2(h)                   (input of final_layer_norm)
+    op_t* ffn_h;    // frames x 3072: GELU(fc1) of THIS layer (train mode: the fc2 weight gradient needs it) or nullptr
 };
 
 struct Workspace {
     bool save;
+    bool train;          // save mode + what the parameter gradients need (per-layer FFN activations)
     UttMeta* meta;       // [B]
     uint32_t* attn_items;  // [Plan::attn_items.size()] work list of the attention kernel
     double* stat_part;   // [B][max_chunks][65]
@@ -169,7 +171,7 @@ struct Handle {
 };
 
 int make_plan(const int64_t* sample_offsets, int B, Plan* plan);
-size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save);
+size_t carve_workspace(const Plan& p, void* base, Workspace* ws, bool save, bool train = false);
 // Host-buffer entry points copy the waveform in utterance groups on a side stream; the front end (statistics, conv0,
 // conv1) of group g then runs while group g + 1 is still crossing PCIe.
 struct FrontPipe {

@@ -147,7 +147,7 @@ class _NomadLossFn(torch.autograd.Function):
 class Nomad():
     def __init__(self, device=None, checkpoint: Optional[str] = None, seed: int = 1234,
                  feature_grad_mult: float = 0.1, max_batch_seconds: float = 2000.0, state_dict=None,
-                 precision: Optional[str] = None):
+                 precision: Optional[str] = None, keep_state_dict: bool = False):
         # *** DEVICE SETTINGS *** (nomad.py:38-49)
         if torch.cuda.is_available():
             self.DEVICE = 'cuda'
@@ -171,6 +171,7 @@ class Nomad():
         # reference's fp32 arithmetic) or "fp32" (split operands, within 1e-5); the loss path always runs "fp16"
         self.precision = precision or os.environ.get("NOMAD_B200_PRECISION", "fp16")
         self.engine = Engine(state_dict, index, self.precision)
+        self.state_dict_ref = state_dict if keep_state_dict else None   # fine-tuning (triplet.py) needs the fp32 tensors
         self.model = TripletModel(self.engine)
         # NOMAD loss model shares the same network (nomad.py:70-72)
         self.lossnet_layers = LossNetLayers(self.engine)

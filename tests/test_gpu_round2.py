@@ -335,3 +335,50 @@ def test_split_operand_gemm_against_fp64(M, N, K, record):
     e2 = float((ch.double() + cl.double() - ref).abs().max()) / scale
     record("split_operand_gemm", M=M, N=N, K=K, rel_err_f32_out=e1, rel_err_split_out=e2)
     assert e1 <= 3e-6 and e2 <= 3e-6
+
+
+# ------------------------------------------------------- triplet fine-tuning step (train_triplet.py:92-133)
+def test_triplet_step_gradients_against_autograd(record):
+    """Loss and EVERY trainable parameter gradient of one triplet step (conv encoder frozen) against torch autograd on
+    the oracle (evaluation mode: the reference's dropout / LayerDrop are stochastic).  Per tensor: relative L2 error
+    <= 3 % and cosine >= 0.999 (fp16 operands in forward, dgrad and wgrad GEMMs); the loss within 1e-3 relative."""
+    from nomad_b200.engine import Engine
+    from nomad_b200.triplet import triplet_loss_and_grads
+    from nomad_b200.weights import random_state_dict
+    from oracle import w2v_oracle as O
+    sd = random_state_dict(1234)
+    sd["embedding_layer.1.weight"] = sd["embedding_layer.1.weight"] * 8.0   # spread the embeddings: active margins
+    eng = Engine(sd, 0)
+    B, N = 3, 24000
+    g = torch.Generator().manual_seed(31)
+    A = 0.1 * torch.randn(B, N, generator=g)
+    P = A + 0.05 * torch.randn(B, N, generator=g)
+    Nn = 0.1 * torch.randn(B, N, generator=g)
+    loss, grads = triplet_loss_and_grads(eng, sd, A, P, Nn, margin=0.2)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sdg = {k: (v.clone().requires_grad_(True) if ("feature_extractor" not in k and not k.endswith("mask_emb")) else v)
+           for k, v in sd.items()}
+    ea, ep, en = O.embed(sdg, A), O.embed(sdg, P), O.embed(sdg, Nn)
+    ref_loss = torch.nn.TripletMarginLoss(margin=0.2)(ea, ep, en)
+    ref_loss.backward()
+    assert ref_loss.item() > 0.0
+    rel_loss = abs(loss.item() - ref_loss.item()) / ref_loss.item()
+    worst_rel, worst_cos, worst_name = 0.0, 1.0, ""
+    missing = []
+    for k, v in sdg.items():
+        if not (torch.is_tensor(v) and v.requires_grad):
+            continue
+        if k not in grads:
+            missing.append(k)
+            continue
+        a, b = grads[k].detach().cpu().reshape(-1).double(), v.grad.reshape(-1).double()
+        rel = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        if rel > worst_rel:
+            worst_rel, worst_name = rel, k
+        worst_cos = min(worst_cos, cos)
+    record("triplet_step", loss=loss.item(), loss_rel_err=rel_loss, worst_grad_rel_l2=worst_rel, worst_tensor=worst_name,
+           worst_grad_cosine=worst_cos, tensors=len(grads))
+    assert not missing, missing
+    assert rel_loss <= 1e-3
+    assert worst_rel <= 3e-2 and worst_cos >= 0.999, (worst_name, worst_rel, worst_cos)
