@@ -107,6 +107,72 @@ __global__ void __launch_bounds__(256) attn_bwd_d_kernel(const op_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// D consistent with the probabilities the backward itself uses: D[q] = sum_j P_qj dP_qj / sum_j P_qj with
+// P = exp(S - lse) recomputed here.  The cheap form above takes O from the forward pass, where it was rounded to
+// 16 bits: the row sums of dS = P (dP - D) are then off by ~5e-4 |dO||O| instead of zero, a first-order error on
+// dQ / dK that swamps them whenever the true gradient wrt the scores is small (nearly uniform attention, or the
+// per-utterance broadcast gradient of a mean-pooled objective: the triplet fine-tuning step).  One extra S / dP
+// pass per query tile; used where parameter gradients are wanted.
+__global__ void __launch_bounds__(128) attn_bwd_dcons_kernel(const op_t* __restrict__ qkv, const op_t* __restrict__ d_out,
+                                                             const float* __restrict__ lse, const UttMeta* __restrict__ meta,
+                                                             float* __restrict__ D) {
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AB;
+    const int T = meta[b].T;
+    if (q0 >= T) return;
+    const long long f0 = meta[b].frame0;
+    __shared__ __align__(128) op_t Qs[AB * 64];
+    __shared__ __align__(128) op_t dOs[AB * 64];
+    __shared__ __align__(128) op_t Ks[AB * 64];
+    __shared__ __align__(128) op_t Vs[AB * 64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    b_load_tile(Qs, qkv, 3 * EMBED, f0, q0, T - 1, h * HEAD_DIM, tid);
+    b_load_tile(dOs, d_out, EMBED, f0, q0, T - 1, h * HEAD_DIM, tid);
+    b_cp_async_wait_all();
+    __syncthreads();
+    uint32_t qf[4][4], dof[4][4];
+    b_load_a_frags(qf, Qs, warp * 16, lane);
+    b_load_a_frags(dof, dOs, warp * 16, lane);
+    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    const int c0 = r0 < T ? r0 : T - 1, c1 = r1 < T ? r1 : T - 1;
+    const float lse0 = lse[(f0 + c0) * HEADS + h], lse1 = lse[(f0 + c1) * HEADS + h];
+    float n0 = 0.f, n1 = 0.f, z0 = 0.f, z1 = 0.f;
+    const int n_tiles = (T + AB - 1) / AB;
+    for (int kt = 0; kt < n_tiles; ++kt) {
+        __syncthreads();
+        b_load_tile(Ks, qkv, 3 * EMBED, f0, kt * AB, T - 1, EMBED + h * HEAD_DIM, tid);
+        b_load_tile(Vs, qkv, 3 * EMBED, f0, kt * AB, T - 1, 2 * EMBED + h * HEAD_DIM, tid);
+        b_cp_async_wait_all();
+        __syncthreads();
+        float s[8][4], dp[8][4];
+        b_zero(s);
+        b_zero(dp);
+        b_mma_nt(s, qf, Ks, lane);
+        b_mma_nt(dp, dof, Vs, lane);
+        const int key_base = kt * AB + 2 * (lane & 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k0 = key_base + i * 8;
+            const bool v0 = k0 < T, v1 = k0 + 1 < T;
+            const float p0 = v0 ? __expf(s[i][0] - lse0) : 0.f, p1 = v1 ? __expf(s[i][1] - lse0) : 0.f;
+            const float p2 = v0 ? __expf(s[i][2] - lse1) : 0.f, p3 = v1 ? __expf(s[i][3] - lse1) : 0.f;
+            n0 = fmaf(p0, dp[i][0], fmaf(p1, dp[i][1], n0));
+            n1 = fmaf(p2, dp[i][2], fmaf(p3, dp[i][3], n1));
+            z0 += p0 + p1;
+            z1 += p2 + p3;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        n0 += __shfl_xor_sync(0xffffffffu, n0, o); n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        z0 += __shfl_xor_sync(0xffffffffu, z0, o); z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+    }
+    if ((lane & 3) == 0) {
+        if (r0 < T) D[(f0 + r0) * HEADS + h] = n0 / z0;
+        if (r1 < T) D[(f0 + r1) * HEADS + h] = n1 / z1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dQ: one CTA per (64-query tile, head, utterance)
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const op_t* __restrict__ qkv, const op_t* __restrict__ d_out,
                                                           const float* __restrict__ lse, const float* __restrict__ D,
@@ -248,10 +314,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const op_t* __restric
 }
 
 int launch_attention_bwd(cudaStream_t st, const op_t* qkv, const op_t* attn_out, const op_t* d_out, const float* lse,
-                         float* D, const UttMeta* meta, int B, int max_T, long long frames, op_t* d_qkv) {
-    attn_bwd_d_kernel<<<(unsigned)((frames * HEADS + 7) / 8), 256, 0, st>>>(d_out, attn_out, frames, D);
-    NB_LAUNCHED();
+                         float* D, const UttMeta* meta, int B, int max_T, long long frames, op_t* d_qkv, bool consistent_d) {
     dim3 grid((max_T + AB - 1) / AB, HEADS, B);
+    if (consistent_d) {
+        attn_bwd_dcons_kernel<<<grid, 128, 0, st>>>(qkv, d_out, lse, meta, D);
+    } else {
+        attn_bwd_d_kernel<<<(unsigned)((frames * HEADS + 7) / 8), 256, 0, st>>>(d_out, attn_out, frames, D);
+    }
+    NB_LAUNCHED();
     attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(qkv, d_out, lse, D, meta, d_qkv);
     NB_LAUNCHED();
     attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(qkv, d_out, lse, D, meta, d_qkv);

@@ -16,7 +16,7 @@
 namespace nb {
 
 int launch_attention_bwd(cudaStream_t st, const op_t* qkv, const op_t* attn_out, const op_t* d_out, const float* lse,
-                         float* D, const UttMeta* meta, int B, int max_T, long long frames, op_t* d_qkv);
+                         float* D, const UttMeta* meta, int B, int max_T, long long frames, op_t* d_qkv, bool consistent_d);
 
 // ---------------------------------------------------------------------------------------------
 struct Row768f {
@@ -619,7 +619,7 @@ static int backward_chain(Handle* h, const Workspace& ws, const LossBufs& L, int
             GemmEpilogue e = epi_grad(EPI_OUT_H16, nullptr, nullptr, L.g_attn, nullptr, EMBED);
             NB_TRY(gemm_h16(st, A, Bw, (int)Fe, EMBED, EMBED, 1, e, impl));
         }
-        NB_TRY(launch_attention_bwd(st, Lb.qkv, Lb.attn, L.g_attn, Lb.lse, L.D, ws.meta, B, T, Fe, L.g_qkv));
+        NB_TRY(launch_attention_bwd(st, Lb.qkv, Lb.attn, L.g_attn, Lb.lse, L.D, ws.meta, B, T, Fe, L.g_qkv, tc != nullptr));
         if (tc) NB_TRY(train_hook_layer(h, ws, L, tc, l, 3, B, Fe, g_running, st));  // fused q/k/v weight + bias
         {   // fused q/k/v dgrad + residual branch -> gradient wrt this layer's input
             GemmOperand A{L.g_qkv, Fe, 3 * EMBED, 0, 0};

@@ -340,45 +340,82 @@ def test_split_operand_gemm_against_fp64(M, N, K, record):
 # ------------------------------------------------------- triplet fine-tuning step (train_triplet.py:92-133)
 def test_triplet_step_gradients_against_autograd(record):
     """Loss and EVERY trainable parameter gradient of one triplet step (conv encoder frozen) against torch autograd on
-    the oracle (evaluation mode: the reference's dropout / LayerDrop are stochastic).  Per tensor: relative L2 error
-    <= 3 % and cosine >= 0.999 (fp16 operands in forward, dgrad and wgrad GEMMs); the loss within 1e-3 relative."""
+    the oracle (evaluation mode: the reference's dropout / LayerDrop are stochastic).  fp16 operands in forward, dgrad and
+    wgrad GEMMs.  Per tensor: ||ours - ref|| <= 3 % of ||ref|| + 0.1 % of the median tensor-gradient norm (the q / k
+    projections of the top layers receive gradients 1000x smaller than everything else under a mean-pooled objective),
+    cosine >= 0.995; all gradients as one vector: relative error <= 2.5 %, cosine >= 0.9997; loss within 1e-3."""
     from nomad_b200.engine import Engine
     from nomad_b200.triplet import triplet_loss_and_grads
     from nomad_b200.weights import random_state_dict
     from oracle import w2v_oracle as O
     sd = random_state_dict(1234)
-    sd["embedding_layer.1.weight"] = sd["embedding_layer.1.weight"] * 8.0   # spread the embeddings: active margins
     eng = Engine(sd, 0)
-    B, N = 3, 24000
+    B, N, MARGIN = 4, 6000, 0.5
     g = torch.Generator().manual_seed(31)
     A = 0.1 * torch.randn(B, N, generator=g)
-    P = A + 0.05 * torch.randn(B, N, generator=g)
+    P = A + 0.1 * torch.randn(B, N, generator=g)    # positives: the anchor at 0 dB SNR
     Nn = 0.1 * torch.randn(B, N, generator=g)
-    loss, grads = triplet_loss_and_grads(eng, sd, A, P, Nn, margin=0.2)
+    loss, grads = triplet_loss_and_grads(eng, sd, A, P, Nn, margin=MARGIN)
     torch.set_num_threads(os.cpu_count() or 1)
     sdg = {k: (v.clone().requires_grad_(True) if ("feature_extractor" not in k and not k.endswith("mask_emb")) else v)
            for k, v in sd.items()}
     ea, ep, en = O.embed(sdg, A), O.embed(sdg, P), O.embed(sdg, Nn)
-    ref_loss = torch.nn.TripletMarginLoss(margin=0.2)(ea, ep, en)
+    ref_loss = torch.nn.TripletMarginLoss(margin=MARGIN)(ea, ep, en)
     ref_loss.backward()
-    assert ref_loss.item() > 0.0
+    hinge = ((ea - ep + 1e-6).norm(dim=1) - (ea - en + 1e-6).norm(dim=1) + MARGIN).detach()
+    # the hinge is a discontinuity of the gradient: every triplet must sit clearly on one side of it
+    assert ref_loss.item() > 0.0 and float(hinge.abs().min()) > 0.02
     rel_loss = abs(loss.item() - ref_loss.item()) / ref_loss.item()
-    worst_rel, worst_cos, worst_name = 0.0, 1.0, ""
-    missing = []
-    for k, v in sdg.items():
-        if not (torch.is_tensor(v) and v.requires_grad):
+    names = [k for k, v in sdg.items() if torch.is_tensor(v) and v.requires_grad]
+    missing = [k for k in names if k not in grads]
+    assert not missing, missing
+    ours = {k: grads[k].detach().cpu().reshape(-1).double() for k in names}
+    ref = {k: sdg[k].grad.reshape(-1).double() for k in names}
+    med = float(torch.tensor([float(ref[k].norm()) for k in names]).median())
+    worst_rel, worst_cos, worst_name, table = 0.0, 1.0, "", []
+    for k in names:
+        a, b = ours[k], ref[k]
+        if k.endswith("k_proj.bias"):
+            # softmax is invariant to a constant added to every key: this gradient is exactly zero (autograd gives
+            # ~1e-10 noise); ours must vanish against the floor
+            assert float(a.norm()) <= 1e-3 * med, (k, float(a.norm()), med)
             continue
-        if k not in grads:
-            missing.append(k)
-            continue
-        a, b = grads[k].detach().cpu().reshape(-1).double(), v.grad.reshape(-1).double()
-        rel = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        diff = float((a - b).norm())
+        rel = diff / float(b.norm().clamp_min(1e-30))
         cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        table.append((rel, cos, k, float(b.norm()), diff))
+        assert diff <= 3e-2 * float(b.norm()) + 1e-3 * med and cos >= 0.995, (k, rel, cos, float(b.norm()), med)
         if rel > worst_rel:
             worst_rel, worst_name = rel, k
         worst_cos = min(worst_cos, cos)
-    record("triplet_step", loss=loss.item(), loss_rel_err=rel_loss, worst_grad_rel_l2=worst_rel, worst_tensor=worst_name,
-           worst_grad_cosine=worst_cos, tensors=len(grads))
-    assert not missing, missing
+    for rel, cos, k, nb, diff in sorted(table, reverse=True)[:8]:
+        print(f"GRAD {rel:10.3e} cos {cos:.6f}  |ref| {nb:.3e} |diff| {diff:.3e}  {k}")
+    keep = [k for k in names if not k.endswith("k_proj.bias")]
+    va, vb = torch.cat([ours[k] for k in keep]), torch.cat([ref[k] for k in keep])
+    g_rel = float((va - vb).norm() / vb.norm())
+    g_cos = float((va @ vb) / (va.norm() * vb.norm()))
+    record("triplet_step", loss=loss.item(), loss_rel_err=rel_loss, all_grads_rel_l2=g_rel, all_grads_cosine=g_cos,
+           worst_tensor_rel_l2=worst_rel, worst_tensor=worst_name, worst_tensor_cosine=worst_cos, tensors=len(names),
+           median_tensor_grad_norm=med)
     assert rel_loss <= 1e-3
-    assert worst_rel <= 3e-2 and worst_cos >= 0.999, (worst_name, worst_rel, worst_cos)
+    assert g_rel <= 2.5e-2 and g_cos >= 0.9997
+
+
+def test_triplet_trainer_step_lowers_the_loss():
+    """``TripletTrainer.step`` (three forwards + loss + gradients in the library, Adam + weight rebuild on the host):
+    repeating the step on one batch lowers that batch's loss, and the updated weights are the ones scoring uses."""
+    from nomad_b200.nomad import Nomad
+    from nomad_b200.triplet import TripletTrainer, triplet_loss_and_grads
+    from nomad_b200.weights import random_state_dict
+    sd = random_state_dict(1234)
+    nomad = Nomad(state_dict=sd, keep_state_dict=True)
+    tr = TripletTrainer(nomad, lr=1e-3, margin=0.5, lr_pretrained=1e-4)
+    g = torch.Generator().manual_seed(5)
+    A = 0.1 * torch.randn(4, 6000, generator=g)
+    P = A + 0.1 * torch.randn(4, 6000, generator=g)
+    Nn = 0.1 * torch.randn(4, 6000, generator=g)
+    e0 = nomad.model(A).clone()
+    losses = [tr.step(A, P, Nn) for _ in range(4)]
+    final, _ = triplet_loss_and_grads(nomad.engine, tr.master, A, P, Nn, margin=0.5)
+    assert final.item() < losses[0] - 1e-3, (losses, final.item())
+    assert float((nomad.model(A) - e0).abs().max()) > 1e-4   # scoring now runs the fine-tuned weights
