@@ -198,6 +198,16 @@ NOMAD_B200_API int64_t nomad_b200_ingest_out_samples(int64_t n_frames, int sr, i
 NOMAD_B200_API int nomad_b200_ingest_pcm16(const int16_t* pcm_dev, int64_t n_frames, int channels, int sr, int target_sr, int trim,
                             float* out_dev, void* stream);
 
+/* Decode step of ``load_processing`` (``torchaudio.load``, nomad.py:196) for 16-bit PCM RIFF/WAVE files, on `threads` host
+ * threads (0 = all cores), no GPU involved.  ``wav_probe`` parses the headers: frames[i] = -1 marks a file that is not
+ * plain 16-bit PCM (the caller decodes it some other way).  ``wav_read_pcm16`` then reads n_samples[i] (= frames x channels)
+ * interleaved samples of file i, starting at data_offset[i], into dst + dst_offset[i] -- e.g. a pinned staging buffer
+ * laid out in batch order, so the whole batch crosses PCIe in one copy. */
+NOMAD_B200_API int nomad_b200_wav_probe(const char* const* paths, int64_t n, int32_t* sample_rate, int32_t* channels,
+                         int64_t* frames, int64_t* data_offset, int threads);
+NOMAD_B200_API int nomad_b200_wav_read_pcm16(const char* const* paths, int64_t n, const int64_t* data_offset,
+                              const int64_t* n_samples, const int64_t* dst_offset, int16_t* dst, int threads);
+
 /* The attention core of one encoder layer, softmax(Q K^T) V per (utterance, head) (fairseq
  * MultiheadAttention inside TransformerSentenceEncoderLayer; mirror torchaudio components.py:237-330).
  * qkv: frames x 2304 op_t device (q | k | v per row, q already scaled by head_dim^-0.5); utterance u owns rows

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "nomad_b200_paired_dist": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "nomad_b200_ingest_out_samples": (c_i64, [c_i64, C.c_int, C.c_int, C.c_int]),
     "nomad_b200_ingest_pcm16": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "nomad_b200_wav_probe": (C.c_int, [C.POINTER(C.c_char_p), c_i64, c_vp, c_vp, c_vp, c_vp, C.c_int]),
+    "nomad_b200_wav_read_pcm16": (C.c_int, [C.POINTER(C.c_char_p), c_i64, c_vp, c_vp, c_vp, c_vp, C.c_int]),
     "nomad_b200_attention_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_int32), C.c_int]),
     "nomad_b200_attention_f16": (C.c_int, [c_vp, c_i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, c_vp, c_vp,
                                             c_vp, C.c_size_t, c_vp]),
@@ -117,3 +119,25 @@ def write_scores_csv(path, index_name, row_labels, col_labels, values, decimals=
     check(load().nomad_b200_write_scores_csv(str(path).encode("utf-8"), str(index_name).encode("utf-8"), rl, n, cl, m,
                                              values.ctypes.data_as(c_vp), int(decimals), int(threads)),
           "nomad_b200_write_scores_csv")
+
+
+def wav_probe(paths, threads=0):
+    """-> (sample_rate int32[n], channels int32[n], frames int64[n] (-1: not 16-bit PCM wav), data_offset int64[n])"""
+    import numpy as np
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[str(p).encode("utf-8") for p in paths])
+    sr, ch = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    fr, off = np.full(n, -1, np.int64), np.zeros(n, np.int64)
+    check(load().nomad_b200_wav_probe(arr, n, sr.ctypes.data_as(c_vp), ch.ctypes.data_as(c_vp), fr.ctypes.data_as(c_vp),
+                                     off.ctypes.data_as(c_vp), int(threads)), "nomad_b200_wav_probe")
+    return sr, ch, fr, off
+
+
+def wav_read_pcm16(paths, data_offset, n_samples, dst_offset, dst_ptr, threads=0):
+    """Read the samples of every file into (int16*) dst_ptr + dst_offset[i] with host threads."""
+    import numpy as np
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[str(p).encode("utf-8") for p in paths])
+    a = [np.ascontiguousarray(x, dtype=np.int64) for x in (data_offset, n_samples, dst_offset)]
+    check(load().nomad_b200_wav_read_pcm16(arr, n, a[0].ctypes.data_as(c_vp), a[1].ctypes.data_as(c_vp),
+                                          a[2].ctypes.data_as(c_vp), c_vp(dst_ptr), int(threads)), "nomad_b200_wav_read_pcm16")

@@ -232,6 +232,23 @@ class Engine:
                        "nomad_b200_ingest_pcm16")
         return self.embed_packed(wav, self.offsets(lens), out)
 
+    def embed_pcm16_mono_files(self, paths, data_offset, frames, threads: int = 0, out: Optional[torch.Tensor] = None):
+        """Same as :meth:`embed_pcm16_mono` with the samples read straight from 16 kHz mono 16-bit wav files into the pinned
+        staging buffer by the library's host threads (``nomad_b200_wav_read_pcm16``): no per-file Python work."""
+        lens = [int(n) for n in frames]
+        total = sum(lens)
+        stage = self.pinned(2 * total)
+        dst = np.zeros(len(lens), dtype=np.int64)
+        np.cumsum(lens[:-1], out=dst[1:])
+        _lib.wav_read_pcm16(paths, data_offset, lens, dst, stage.data_ptr(), threads)
+        dev = stage[: 2 * total].view(torch.int16).to(self.device, non_blocking=True)
+        self.pinned_release()
+        wav = torch.empty((total,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_ingest_pcm16(_ptr(dev), total, 1, 16000, 16000, 0, _ptr(wav), _stream_ptr()),
+                       "nomad_b200_ingest_pcm16")
+        return self.embed_packed(wav, self.offsets(lens), out)
+
     # ------------------------------------------------------------------ ingest
     def ingest_pcm16(self, pcm: np.ndarray, sr: int, target_sr: int = 16000, trim: bool = False) -> torch.Tensor:
         """``load_processing`` on the device: (n_frames, channels) or (n_frames,) int16 HOST samples at ``sr`` ->

@@ -310,40 +310,61 @@ class Nomad():
 
     def embed_files(self, filepaths: Sequence, root=False) -> torch.Tensor:
         """The reference's per-file loop (``nomad.py:172-186``) restructured for throughput -> (n, 256) CUDA tensor in
-        input order.  Files are read in windows of ``self.window_files`` (bounded memory for 100 k-file corpora) by a
-        small thread pool, every window is length-bucketed into batches, and the GPU works on window k while the host
-        reads window k + 1 (no per-batch synchronisation; the returned tensor may still be being computed)."""
+        input order.  Files are handled in windows of ``self.window_files`` (bounded memory for 100 k-file corpora).
+        Per window the headers of all files are parsed by the library's host threads (``nomad_b200_wav_probe``); 16 kHz
+        mono 16-bit PCM files -- the common corpus format -- are then read batch by batch straight into a pinned
+        staging buffer (``nomad_b200_wav_read_pcm16``), cross PCIe as 16-bit samples in ONE copy per batch and are
+        converted on the GPU in one launch; everything else takes the per-file path (device resampling for other PCM16
+        wavs, ``load_processing`` for other formats).  Nothing synchronises per batch: the GPU works on batch k while
+        the host reads batch k + 1 (the returned tensor may still be being computed)."""
         from concurrent.futures import ThreadPoolExecutor
+
+        from . import _lib
         n_files = len(filepaths)
         parts = []
         with ThreadPoolExecutor(max_workers=self.reader_threads) as pool:
             for w0 in range(0, n_files, self.window_files):
                 paths = []
                 for filename_anchor in filepaths[w0:w0 + self.window_files]:
-                    if root:
-                        paths.append(os.path.join(root, filename_anchor if not isinstance(filename_anchor, np.ndarray) else filename_anchor[0]))
-                    else:
-                        paths.append(filename_anchor)
-                items = list(pool.map(self._read_for_embed, paths))
+                    if isinstance(filename_anchor, np.ndarray):
+                        filename_anchor = filename_anchor[0]  # nomad.py:194-195: a DataFrame row
+                    paths.append(os.path.join(root, filename_anchor) if root else filename_anchor)
+                paths = [str(p) for p in paths]
+                if self.device_ingest:
+                    sr, ch, frames, data_off = _lib.wav_probe(paths, self.reader_threads)
+                    fast = (frames >= 0) & (sr == 16000) & (ch == 1)
+                else:
+                    frames = np.full(len(paths), -1, np.int64)
+                    data_off = np.zeros(len(paths), np.int64)
+                    fast = np.zeros(len(paths), bool)
+                slow_idx = [i for i in range(len(paths)) if not fast[i]]
+                items = dict(zip(slow_idx, pool.map(self._read_for_embed, [paths[i] for i in slow_idx])))
                 lengths = []
-                for k, (kind, v) in enumerate(items):
-                    if kind == "dev":   # 16-bit PCM at another rate / stereo: mix + resample on the GPU, per file
-                        items[k] = (kind, v) = ("wav", self.engine.ingest_pcm16(v[0], v[1], 16000, False))
-                    n = int(v.shape[-1]) if kind == "wav" else int(v.shape[0])
+                for k in range(len(paths)):
+                    if fast[k]:
+                        n = int(frames[k])
+                    else:
+                        kind, v = items[k]
+                        if kind == "dev":   # 16-bit PCM at another rate / stereo: mix + resample on the GPU, per file
+                            items[k] = (kind, v) = ("wav", self.engine.ingest_pcm16(v[0], v[1], 16000, False))
+                        n = int(v.shape[-1]) if kind == "wav" else int(v.shape[0])
                     if n < MIN_SAMPLES:
                         raise RuntimeError(f"Calculated padded input size per channel: ({n}). Kernel size: (10). "
                                            "Kernel size can't be greater than actual input size")
                     lengths.append(n)
-                dev_out = torch.empty((len(items), EMB_DIM), dtype=torch.float32, device=self.engine.device)
+                dev_out = torch.empty((len(paths), EMB_DIM), dtype=torch.float32, device=self.engine.device)
                 for idx in plan_batches(lengths, self.max_batch_samples):
                     sel = torch.as_tensor(idx, device=self.engine.device)
-                    if all(items[i][0] == "pcm" for i in idx):
-                        dev_out[sel] = self.engine.embed_pcm16_mono([items[i][1] for i in idx])
-                    else:
-                        waves = [items[i][1].reshape(-1) if items[i][0] == "wav"
-                                 else torch.from_numpy(items[i][1].astype(np.float32) / 32768.0) for i in idx]
-                        dev_out[sel] = self.engine.embed(waves)
-                parts.append(dev_out)  # still being computed; the host goes on reading the next window
+                    if all(fast[i] for i in idx):
+                        dev_out[sel] = self.engine.embed_pcm16_mono_files([paths[i] for i in idx], data_off[idx], frames[idx],
+                                                                          self.reader_threads)
+                        continue
+                    waves = []
+                    for i in idx:   # mixed batch (rare): the fast files take the per-file path too
+                        kind, v = items[i] if i in items else self._read_for_embed(paths[i])
+                        waves.append(v.reshape(-1) if kind == "wav" else torch.from_numpy(v.astype(np.float32) / 32768.0))
+                    dev_out[sel] = self.engine.embed(waves)
+                parts.append(dev_out)  # still being computed; the host goes on with the next window
         if not parts:
             return torch.zeros((0, EMB_DIM), dtype=torch.float32, device=self.engine.device)
         return torch.cat(parts) if len(parts) > 1 else parts[0]

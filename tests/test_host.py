@@ -171,3 +171,34 @@ def test_csv_writer_fuzz_against_pandas(tmp_path):
         ref.to_csv(p_ref, index=False)
         _lib.write_scores_csv(p_got, "Test File", rows, cols, values, decimals=decimals, threads=2)
         assert p_got.read_bytes() == p_ref.read_bytes(), decimals
+
+
+def test_native_wav_reader_against_the_wave_module(tmp_path):
+    """``nomad_b200_wav_probe`` / ``nomad_b200_wav_read_pcm16`` (host threads, no GPU): headers and samples equal what
+    the ``wave`` module reads; anything that is not plain 16-bit PCM is reported as not handled (frames = -1)."""
+    import wave
+
+    from nomad_b200 import _lib
+    rng = np.random.default_rng(0)
+    paths, data = [], []
+    for i, (sr, ch, n) in enumerate([(16000, 1, 5000), (44100, 2, 3001), (16000, 1, 1), (8000, 1, 0), (48000, 1, 70001)]):
+        p = str(tmp_path / f"f{i}.wav")
+        pcm = (rng.standard_normal((n, ch)) * 3000).astype(np.int16)
+        with wave.open(p, "wb") as w:
+            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(sr); w.writeframes(pcm.tobytes())
+        paths.append(p); data.append(pcm)
+    (tmp_path / "bad.wav").write_bytes(b"not a wav file at all")
+    with wave.open(str(tmp_path / "f8.wav"), "wb") as w:       # 8-bit PCM: not handled natively
+        w.setnchannels(1); w.setsampwidth(1); w.setframerate(16000); w.writeframes(b"\x80" * 100)
+    paths += [str(tmp_path / "bad.wav"), str(tmp_path / "missing.wav"), str(tmp_path / "f8.wav")]
+    sr, ch, fr, off = _lib.wav_probe(paths, 3)
+    assert list(sr[:5]) == [16000, 44100, 16000, 8000, 48000] and list(ch[:5]) == [1, 2, 1, 1, 1]
+    assert list(fr) == [5000, 3001, 1, 0, 70001, -1, -1, -1]
+    ns = np.array([max(f, 0) * c for f, c in zip(fr, ch)], np.int64)
+    dst = np.zeros(len(paths), np.int64)
+    np.cumsum(ns[:-1], out=dst[1:])
+    buf = np.full(int(ns.sum()) + 4, 12345, np.int16)
+    _lib.wav_read_pcm16(paths, off, ns, dst, buf.ctypes.data, 4)
+    for i, pcm in enumerate(data):
+        np.testing.assert_array_equal(buf[dst[i]: dst[i] + ns[i]], pcm.reshape(-1))
+    assert (buf[int(ns.sum()):] == 12345).all()
