@@ -1213,6 +1213,8 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
         if (spec && fl == F_CONV_SAVE) return launch_pair_impl<16, false, false, F_CONV_SAVE>(st, A, B, args);
         return launch_pair_impl<16, false>(st, A, B, args);
     }
+    // Measured and dropped (round 2, profiles/r02_experiments.md): this epilogue on 16 warps without the residual prefetch
+    // buffer (96-register budget: 100 B of spills) runs out-proj at 192-212 us instead of 139 us.
     static const int rpf = getenv("NOMAD_B200_RESID_PREFETCH") ? atoi(getenv("NOMAD_B200_RESID_PREFETCH")) : 1;
     if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) {
         if (spec && fl == F_RES) return launch_pair_impl<8, false, true, F_RES>(st, A, B, args);
