@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -786,6 +787,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, cluster
+    // sync) ran while the previous kernel of the stream was still draining its last tiles; from here on this kernel reads
+    // what that kernel wrote.  (No-ops when the kernel was launched without the attribute.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1177,7 +1183,23 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
         if (e.flags & EPI_OUT_H16) NB_TRY(make_store_map(&tmH, e.out_h, false, args.M, args.N, e.ldo));
         if (e.flags & EPI_SAVE_DGELU) NB_TRY(make_store_map(&tmX, e.aux_out, false, args.M, args.N, e.ldo));
     }
-    gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args);
+    static const int pdl = getenv("NOMAD_B200_PDL") ? atoi(getenv("NOMAD_B200_PDL")) : 1;
+    if (pdl) {  // programmatic dependent launch: this kernel's prologue overlaps the tail of the previous kernel
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(128 + 32 * NEW);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        NB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS>, tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args));
+    } else {
+        gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args);
+    }
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
     return 0;
