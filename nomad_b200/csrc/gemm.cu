@@ -38,6 +38,10 @@ struct GemmArgs {
     int umma_n;  // N of the MMA instruction (<= BN, multiple of 16)
     int m_tiles, n_tiles;
     int a_wrap;  // GemmOperand::k_wrap of A
+    // "shared operand" batching (single-CTA kernel): every batch reads the SAME A / B tensor (batch coordinate 0) and the
+    // B operand's K origin moves by b_kshift0 + batch * b_kshift_step elements (negative / past-the-end columns read as
+    // zero): batch = tap of a correlation sum_k A[m, k] B[n, k + tap] (the positional conv's weight gradient)
+    int shared_ab, b_kshift0, b_kshift_step, b_mod;  // B batch coordinate = batch % b_mod, K shift = b_kshift0 + (batch / b_mod) * step
     unsigned sleep_ns;  // back-off of the waiting TMA / MMA role threads (0 = spin); they share schedulers with epilogue warps
     GemmEpilogue epi;
 };
@@ -627,9 +631,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int kk = kb * BK;
                         tma_load_3d(sa, mA, &full_bar[stage], kk % args.a_wrap, m_blk * BM + kk / args.a_wrap, b);
                     } else {
-                        tma_load_3d(sa, mA, &full_bar[stage], kb * BK, m_blk * BM, b);
+                        tma_load_3d(sa, mA, &full_bar[stage], kb * BK, m_blk * BM, args.shared_ab ? 0 : b);
                     }
-                    tma_load_3d(sb, mB, &full_bar[stage], kb * BK, n_blk * BN, b);
+                    tma_load_3d(sb, mB, &full_bar[stage],
+                                kb * BK + (args.shared_ab ? args.b_kshift0 + (b / args.b_mod) * args.b_kshift_step : 0), n_blk * BN,
+                                args.shared_ab ? b % args.b_mod : b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -1089,13 +1095,17 @@ static int launch_tc_impl(cudaStream_t st, const GemmOperand& A, const GemmOpera
         *flag = true;
     }
     CUtensorMap tmA, tmB, tmA2, tmB2;
-    NB_TRY(make_operand_map(&tmA, A, args.K, args.batch, BM));
-    NB_TRY(make_operand_map(&tmB, B, args.K, args.batch, args.umma_n));
+    // shared-operand batching: one tensor per operand (no batch dimension); B's map spans its whole row so that the
+    // per-batch K shift reads zeros outside it
+    const int mb = args.shared_ab ? 1 : args.batch;
+    const int kb_ext = args.shared_ab ? (int)B.row_stride : args.K;
+    NB_TRY(make_operand_map(&tmA, A, args.K, mb, BM));
+    NB_TRY(make_operand_map(&tmB, B, kb_ext, args.shared_ab ? args.b_mod : mb, args.umma_n));
     GemmOperand Al, Bl;
     lo_operand(A, &Al);
     lo_operand(B, &Bl);
-    NB_TRY(make_operand_map(&tmA2, Al, args.K, args.batch, BM));
-    NB_TRY(make_operand_map(&tmB2, Bl, args.K, args.batch, args.umma_n));
+    NB_TRY(make_operand_map(&tmA2, Al, args.K, mb, BM));
+    NB_TRY(make_operand_map(&tmB2, Bl, kb_ext, args.shared_ab ? args.b_mod : mb, args.umma_n));
     args.m_tiles = (args.M + BM - 1) / BM;
     args.n_tiles = (args.N + BN - 1) / BN;
     const long long tiles = (long long)args.m_tiles * args.n_tiles * args.batch;
@@ -1250,6 +1260,22 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     return launch_pair_impl<8, false>(st, A, B, args);
 }
 
+static thread_local int g_corr_shift0 = 0, g_corr_step = 0, g_corr_on = 0, g_corr_mod = 1;
+
+// C[b] = epilogue(sum_k A[m, k] B_{b % b_mod}[n, k + shift0 + (b / b_mod) * step]) for b in [0, batch): ONE A tensor shared by
+// all batches, b_mod B tensors (B.batch_stride apart), the B operand's K origin shifted per batch (columns outside the row read
+// as zero).  TMA needs the shifted origin 16-byte aligned: shift0 and step must be multiples of 8 elements -- a caller that
+// needs every shift keeps 8 copies of B pre-shifted by 0..7 elements (b_mod = 8).  N <= 128 (single-CTA kernel).
+int gemm_h16_corr(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch, int shift0,
+                  int step, int b_mod, const GemmEpilogue& epi) {
+    NB_CHECK(N <= 128, "gemm_h16_corr: N <= 128");
+    NB_CHECK(shift0 % 8 == 0 && step % 8 == 0 && b_mod >= 1, "gemm_h16_corr: shifts must be multiples of 8 elements");
+    g_corr_on = 1; g_corr_shift0 = shift0; g_corr_step = step; g_corr_mod = b_mod;
+    const int rc = gemm_h16(st, A, B, M, N, K, batch, epi, 0);
+    g_corr_on = 0;
+    return rc;
+}
+
 int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
@@ -1259,6 +1285,7 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
     args.epi = epi;
     args.umma_n = 0; args.m_tiles = args.n_tiles = 0;
     args.a_wrap = A.k_wrap;
+    args.shared_ab = g_corr_on; args.b_kshift0 = g_corr_shift0; args.b_kshift_step = g_corr_step; args.b_mod = g_corr_mod;
     static const unsigned sleep_ns = getenv("NOMAD_B200_GEMM_SLEEP") ? (unsigned)atoi(getenv("NOMAD_B200_GEMM_SLEEP")) : 0u;
     args.sleep_ns = sleep_ns;
     NB_CHECK(B.k_wrap == 0, "only the A operand may use wrapped K");

@@ -86,6 +86,12 @@ static constexpr int LN_PARTS = 12;  // 768 / 64
 int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch,
               const GemmEpilogue& epi, int impl);
 
+// C[b] = epilogue(sum_k A[m, k] B_{b % b_mod}[n, k + shift0 + (b / b_mod) * step]): ONE A tensor shared by all batches, b_mod B
+// tensors B.batch_stride apart, B's K origin shifted per batch (out-of-range columns read as zero; shifts multiples of 8
+// elements: TMA wants 16-byte aligned origins); B.row_stride = B's full row length.  N <= 128.
+int gemm_h16_corr(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int batch, int shift0,
+                  int step, int b_mod, const GemmEpilogue& epi);
+
 int device_sm_count();
 // column groups (partial row sums per row) the EPI_CDIST tensor-core kernels write for an n x m problem
 int cdist_row_groups(long long n, long long m);

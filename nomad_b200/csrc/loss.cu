@@ -740,24 +740,26 @@ struct TrainCtx {
     long long Fp;     // tokens rounded up to 8 (K of the weight-gradient GEMMs)
 };
 
-// in [rows][cols] (16-bit) -> out [cols][rows_p], columns rows..rows_p-1 zero
+// in [rows][cols] (16-bit) -> out[z][cols][rows_p] with out[z][c][r] = in[r + z][c] (zero past the end): copy z is the
+// transpose shifted by z rows (copies = 1: the plain transpose, columns rows..rows_p-1 zero)
 __global__ void __launch_bounds__(256) transpose_h16_kernel(const op_t* __restrict__ in, long long rows, int cols,
                                                             long long rows_p, op_t* __restrict__ out) {
     __shared__ op_t tile[64][66];
     const long long r0 = (long long)blockIdx.x * 64;
-    const int c0 = blockIdx.y * 64;
+    const int c0 = blockIdx.y * 64, z = blockIdx.z;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int r = i >> 6, c = i & 63;
-        tile[r][c] = (r0 + r < rows && c0 + c < cols) ? in[(r0 + r) * cols + c0 + c] : f2op(0.f);
+        tile[r][c] = (r0 + r + z < rows && c0 + c < cols) ? in[(r0 + r + z) * cols + c0 + c] : f2op(0.f);
     }
     __syncthreads();
+    op_t* o = out + (long long)z * cols * rows_p;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int c = i >> 6, r = i & 63;
-        if (c0 + c < cols && r0 + r < rows_p) out[(long long)(c0 + c) * rows_p + r0 + r] = tile[r][c];
+        if (c0 + c < cols && r0 + r < rows_p) o[(long long)(c0 + c) * rows_p + r0 + r] = tile[r][c];
     }
 }
-static int launch_transpose(cudaStream_t st, const op_t* in, long long rows, int cols, long long rows_p, op_t* out) {
-    dim3 grid((unsigned)((rows_p + 63) / 64), (unsigned)((cols + 63) / 64));
+static int launch_transpose(cudaStream_t st, const op_t* in, long long rows, int cols, long long rows_p, op_t* out, int copies = 1) {
+    dim3 grid((unsigned)((rows_p + 63) / 64), (unsigned)((cols + 63) / 64), copies);
     transpose_h16_kernel<<<grid, 256, 0, st>>>(in, rows, cols, rows_p, out);
     NB_LAUNCHED();
     return 0;
@@ -1078,9 +1080,28 @@ static int train_hook_front(Handle* h, const Workspace& ws, const LossBufs& L, T
     if (stage == 0) {  // encoder LayerNorm params: input x0 + pos_y, incoming gradient L.g_a
         NB_TRY(launch_ln768_param_grad(st, L.g_a, nullptr, ws.x0, ws.pos_y, ws.meta, B, Fe, G + TrainLayout::ENC_G, G + TrainLayout::ENC_B));
     } else if (stage == 1) {  // positional conv (folded weight) + bias: dY = L.pos_g, X = ws.pos_g
-        dim3 grid(POS_K, POS_G);
-        pos_wgrad_kernel<<<grid, 288, 0, st>>>(L.pos_g, ws.pos_g, rows_alloc, pos_rows_e, G + TrainLayout::POS_W);
-        NB_LAUNCHED();
+        // dW[g][n][tap][c] = sum_p dY[g][p][n] X[g][p - 64 + tap][c]: per group, transpose both padded layouts to
+        // [48][rows] (K-major over the rows) and run ONE shared-operand tensor-core GEMM batched over the 128 taps, the
+        // B operand's K origin shifted per tap.  TMA wants 16-byte aligned origins, so X is kept as 8 transposes
+        // pre-shifted by 0..7 rows: tap = 8 q + r reads copy r at origin 8 q - 64 (outside the row reads zero).
+        static const int pos_simt = getenv("NOMAD_B200_POS_WGRAD_SIMT") ? atoi(getenv("NOMAD_B200_POS_WGRAD_SIMT")) : 0;
+        const long long Rp = (rows_alloc + 7) / 8 * 8;
+        if (pos_simt || 8 * (long long)POS_GC * Rp > (long long)FFN * tc->Fp) {  // scratch too small: CUDA-core fallback
+            dim3 grid(POS_K, POS_G);
+            pos_wgrad_kernel<<<grid, 288, 0, st>>>(L.pos_g, ws.pos_g, rows_alloc, pos_rows_e, G + TrainLayout::POS_W);
+            NB_LAUNCHED();
+        } else {
+            for (int g = 0; g < POS_G; ++g) {
+                NB_TRY(launch_transpose(st, L.pos_g + (long long)g * rows_alloc * POS_GC, rows_alloc, POS_GC, Rp, tc->tA));
+                NB_TRY(launch_transpose(st, ws.pos_g + (long long)g * rows_alloc * POS_GC, rows_alloc, POS_GC, Rp, tc->tB, 8));
+                GemmOperand A{tc->tA, POS_GC, Rp, 0, 0};
+                GemmOperand Bw{tc->tB, POS_GC, Rp, (long long)POS_GC * Rp, 0};
+                GemmEpilogue e = epi_linear(EPI_OUT_F32, nullptr, nullptr, G + TrainLayout::POS_W + (long long)g * POS_GC * POS_K * POS_GC,
+                                            nullptr, (long long)POS_K * POS_GC);
+                e.out_bstride = POS_GC;  // batch = tap: columns [tap * 48, tap * 48 + 48) of the [n][tap * 48 + c] rows
+                NB_TRY(gemm_h16_corr(st, A, Bw, POS_GC, POS_GC, (int)Rp, POS_K, -(POS_K / 2), 8, 8, e));
+            }
+        }
         pos_bias_grad_kernel<<<POS_G, 256, 0, st>>>(L.pos_g, rows_alloc, G + TrainLayout::POS_B);
         NB_LAUNCHED();
     } else if (stage == 2) {  // feature projection: dY = L.g_x0h, X = LayerNorm(512) output

@@ -37,6 +37,22 @@ def grad_segments():
     return out
 
 
+_DEV_CACHE: Dict = {}
+
+
+def _device_copy(engine: Engine, state_dict, key: str) -> torch.Tensor:
+    """fp32 copy of a (host) checkpoint tensor on the engine's device, cached per source tensor version: the positional
+    conv's weight_v is 19 MB, and a pageable H2D copy of it per step cost 1.5 ms."""
+    t = state_dict[key]
+    if t.is_cuda:
+        return t.detach().to(torch.float32).clone()
+    tag = (id(t), t._version, engine.device_index)
+    hit = _DEV_CACHE.get(key)
+    if hit is None or hit[0] != tag:
+        _DEV_CACHE[key] = (tag, t.detach().to(engine.device, torch.float32))
+    return _DEV_CACHE[key][1].clone()
+
+
 SHAPES = {"qkv.weight": (2304, 768), "self_attn.out_proj.weight": (768, 768), "fc1.weight": (3072, 768),
           "fc2.weight": (768, 3072), "post_extract_proj.weight": (768, 512), "embedding_layer.1.weight": (256, 768)}
 
@@ -77,8 +93,8 @@ def triplet_loss_and_grads(engine: Engine, state_dict, anchor: torch.Tensor, pos
         elif name.endswith("pos_conv.0.folded_weight"):
             # [g][n][tap][c] -> (out = g * 48 + n, in = c, tap); then through weight_norm(dim=2): w = g * v / ||v||
             dw = g.view(16, 48, 128, 48).permute(0, 1, 3, 2).reshape(768, 48, 128)
-            v = state_dict["ssl_model.encoder.pos_conv.0.weight_v"].to(engine.device, torch.float32).detach().requires_grad_(True)
-            gg = state_dict["ssl_model.encoder.pos_conv.0.weight_g"].to(engine.device, torch.float32).detach().requires_grad_(True)
+            v = _device_copy(engine, state_dict, "ssl_model.encoder.pos_conv.0.weight_v").requires_grad_(True)
+            gg = _device_copy(engine, state_dict, "ssl_model.encoder.pos_conv.0.weight_g").requires_grad_(True)
             w = gg * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
             w.backward(dw)
             grads["ssl_model.encoder.pos_conv.0.weight_v"] = v.grad
