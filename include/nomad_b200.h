@@ -166,6 +166,11 @@ NOMAD_B200_API int nomad_b200_paired_dist(const float* a_dev, const float* b_dev
  * values laid out as nomad_b200_triplet_grad_segment enumerates, all multiplied by *grad_scale_out (a power of two
  * that keeps 16-bit activation gradients in range; divide it out).  The optimiser step itself (Adam, train_triplet.py:
  * 92-107) is host plumbing: see nomad_b200/triplet.py. */
+/* After the optimiser step (train_triplet.py:129-130): rebuild the kernel-ready weights of everything trainable (16-bit
+ * copies, fused q|k|v with the q scale, transposes for the dgrad GEMMs, LayerNorm folds, weight-norm fold of the positional
+ * conv, head) from fp32 master tensors that live on the DEVICE -- same names as nomad_b200_create, `data` = device pointers.
+ * A few bandwidth-bound kernels on `stream`; the frozen conv feature encoder is not touched. */
+NOMAD_B200_API int nomad_b200_refresh_weights(nomad_b200_handle* h, const nomad_b200_tensor* tensors_dev, int n_tensors, void* stream);
 NOMAD_B200_API int64_t nomad_b200_triplet_grad_floats(void);
 NOMAD_B200_API int nomad_b200_triplet_grad_segment(int i, char* name, int name_cap, int64_t* offset, int64_t* numel);
 NOMAD_B200_API size_t nomad_b200_triplet_workspace_bytes(int B, int64_t N);

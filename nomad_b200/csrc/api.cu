@@ -378,6 +378,7 @@ static int build_weights(Handle* h, TensorTable& tt) {
     w.loss_head_wt = nullptr;
     w.loss_head_w = nullptr;
     w.loss_head_b = nullptr;
+    w.pos_scale_tmp = nullptr;
     return 0;
 }
 

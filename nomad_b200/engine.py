@@ -84,6 +84,24 @@ class Engine:
     def _mode(self) -> int:
         return PRECISIONS[self.precision]
 
+    def refresh_weights(self, state_dict_dev):
+        """Rebuild the kernel-ready weights from fp32 master tensors on THIS device (``nomad_b200_refresh_weights``): the step
+        after an optimiser update.  ``state_dict_dev``: {state_dict key: contiguous fp32 CUDA tensor}; conv encoder frozen."""
+        names, ptrs, keep = [], [], []
+        for k, v in state_dict_dev.items():
+            if not torch.is_tensor(v) or k.endswith("mask_emb") or "feature_extractor" in k:
+                continue
+            t = v.detach()
+            assert t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous(), k
+            names.append(k.encode()); ptrs.append(t.data_ptr()); keep.append(t)
+        tens = (_lib.Tensor * len(names))()
+        for i, (n, p_, t) in enumerate(zip(names, ptrs, keep)):
+            tens[i].name = n
+            tens[i].data = C.c_void_p(p_)
+            tens[i].numel = t.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nomad_b200_refresh_weights(self.handle, tens, len(names), _stream_ptr()), "nomad_b200_refresh_weights")
+
     def set_loss_head(self, weight: torch.Tensor, bias: torch.Tensor):
         w = np.ascontiguousarray(weight.detach().to(torch.float32).cpu().numpy())
         b = np.ascontiguousarray(bias.detach().to(torch.float32).cpu().numpy())

@@ -6,12 +6,11 @@ encoder (``freeze_convnet: True``), with lr 1e-5 for the pre-trained network and
 (``:96-104``).  Here the three forwards, the loss and ALL parameter gradients come from one C-ABI call
 (``nomad_b200_triplet_fwd_bwd``: tensor-core forward, dgrad chain, weight-gradient GEMMs); the optimiser state and the
 update are host plumbing (``torch.optim.Adam`` on fp32 master tensors on the GPU), after which the kernel-ready
-weights are rebuilt from the updated state_dict.
+weights are rebuilt on the device from those tensors (``nomad_b200_refresh_weights``).
 
-Differences from the reference, both deliberate: the network runs in evaluation mode (no dropout / LayerDrop: fairseq's
+Deliberate difference from the reference: the network runs in evaluation mode (no dropout / LayerDrop: fairseq's
 ``Wav2Vec2Model`` applies dropout 0.1 and layerdrop 0.05 under ``model.train()``, which makes the reference's step
-stochastic), and the rebuild of the kernel-ready weights after the step is a host-side pass (seconds), so this is a
-correct fine-tuning step, not yet a fast one.
+stochastic).
 """
 from __future__ import annotations
 
@@ -117,7 +116,7 @@ class TripletTrainer:
         for k in train:
             self.master[k].requires_grad_(True)
         self.optim = torch.optim.Adam([{"params": [self.master[k] for k in train if k not in head], "lr": lr_pretrained},
-                                       {"params": [self.master[k] for k in head]}], lr=lr)
+                                       {"params": [self.master[k] for k in head]}], lr=lr, fused=True)
 
     @staticmethod
     def _state_dict(nomad):
@@ -132,12 +131,7 @@ class TripletTrainer:
         for k, g in grads.items():
             self.master[k].grad = g.reshape(self.master[k].shape).contiguous()
         self.optim.step()
-        # rebuild the kernel-ready weights (fp16 copies, folds, transposes) from the updated master copy
-        sd = OrderedDict((k, v.detach()) for k, v in self.master.items())
-        old = self.nomad.engine
-        self.nomad.engine = Engine(sd, old.device_index, old.precision)
-        self.nomad.model.engine = self.nomad.engine
-        self.nomad.lossnet_layers.engine = self.nomad.engine
-        self.nomad.lossnet_layers._synced = None
-        old.close()
+        # rebuild the kernel-ready weights (16-bit copies, q|k|v fusion, transposes, LayerNorm folds, weight-norm fold) from
+        # the updated master tensors, on the device
+        self.nomad.engine.refresh_weights(self.master)
         return float(loss.item())

@@ -419,3 +419,30 @@ def test_triplet_trainer_step_lowers_the_loss():
     final, _ = triplet_loss_and_grads(nomad.engine, tr.master, A, P, Nn, margin=0.5)
     assert final.item() < losses[0] - 1e-3, (losses, final.item())
     assert float((nomad.model(A) - e0).abs().max()) > 1e-4   # scoring now runs the fine-tuned weights
+
+
+def test_device_weight_refresh_equals_a_fresh_handle(state_dict):
+    """``nomad_b200_refresh_weights`` (device-side rebuild of the kernel-ready weights after an optimiser step) against
+    ``nomad_b200_create`` on the same tensors: scoring path (LayerNorm folds, fused q|k|v, positional-conv weight-norm
+    fold, head) and the loss path (plain + transposed copies) give the same results."""
+    from nomad_b200.engine import Engine
+    g = torch.Generator().manual_seed(77)
+    sd2 = {k: (v + 0.01 * v.abs().mean() * torch.randn(v.shape, generator=g) if "feature_extractor" not in k else v.clone())
+           for k, v in state_dict.items()}
+    a = Engine(state_dict, 0)
+    b = Engine(sd2, 0)
+    waves = [0.1 * torch.randn(n, generator=g) for n in (16000, 20481, 4000)]
+    before = a.embed(waves).clone()
+    a.refresh_weights({k: v.cuda().contiguous() for k, v in sd2.items()})
+    ea, eb = a.embed(waves), b.embed(waves)
+    assert float((before - eb).abs().max()) > 1e-4          # the weights really changed
+    assert float((ea - eb).abs().max()) <= 2e-6              # fold sums are fp32 on the device, fp64 on the host
+    hw, hb = 0.03 * torch.randn(256, 768, generator=g), torch.zeros(256)
+    est, cln = 0.1 * torch.randn(2, 8000, generator=g), 0.1 * torch.randn(2, 8000, generator=g)
+    out = []
+    for e in (a, b):
+        e.set_loss_head(hw, hb)
+        l, gr = e.loss_fwd_bwd(est.cuda(), cln.cuda(), 0.1)
+        out.append((float(l), gr.clone()))
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[1][0])
+    assert float((out[0][1] - out[1][1]).abs().max()) <= 1e-6 * float(out[1][1].abs().max())
