@@ -171,6 +171,8 @@ NOMAD_B200_API int nomad_b200_paired_dist(const float* a_dev, const float* b_dev
  * conv, head) from fp32 master tensors that live on the DEVICE -- same names as nomad_b200_create, `data` = device pointers.
  * A few bandwidth-bound kernels on `stream`; the frozen conv feature encoder is not touched. */
 NOMAD_B200_API int nomad_b200_refresh_weights(nomad_b200_handle* h, const nomad_b200_tensor* tensors_dev, int n_tensors, void* stream);
+/* Test hook for the refresh path: copy one kernel-ready weight buffer to the host (see refresh.cu for the names). */
+NOMAD_B200_API int nomad_b200_debug_read_weight(nomad_b200_handle* h, const char* which, void* dst_host, size_t bytes);
 NOMAD_B200_API int64_t nomad_b200_triplet_grad_floats(void);
 NOMAD_B200_API int nomad_b200_triplet_grad_segment(int i, char* name, int name_cap, int64_t* offset, int64_t* numel);
 NOMAD_B200_API size_t nomad_b200_triplet_workspace_bytes(int B, int64_t N);

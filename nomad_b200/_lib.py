@@ -53,6 +53,7 @@ PROTOTYPES = {
     "nomad_b200_gemm_f16": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_vp]),
     "nomad_b200_refresh_weights": (C.c_int, [c_vp, C.POINTER(Tensor), C.c_int, c_vp]),
+    "nomad_b200_debug_read_weight": (C.c_int, [c_vp, C.c_char_p, c_vp, C.c_size_t]),
     "nomad_b200_triplet_grad_floats": (c_i64, []),
     "nomad_b200_triplet_grad_segment": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "nomad_b200_triplet_workspace_bytes": (C.c_size_t, [C.c_int, c_i64]),

@@ -269,6 +269,7 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <int NT>  // 0: row-major tiles + quad shuffles (round 1); 2 / 4: channel-permuted groups of NT tiles, direct stores
 __global__ void __launch_bounds__(256, NB_CONV0_BLOCKS) conv0_mma_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
                                                         int B, int blk0, const float* __restrict__ fold,
                                                         const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(256, NB_CONV0_BLOCKS) conv0_mma_kernel(const f
             a2[mt][2 + k] = pack_op(x[2 * q + 4], x[2 * q + 5]);
         }
     }
+    if constexpr (NT == 0) {
     op_t* obase = out + (long long)(row_base + r) * CONV_DIM + warp * 64 + 4 * q;
     const int src = (lane & ~3) | ((2 * q) & 3);
 #pragma unroll 1
@@ -366,6 +368,59 @@ __global__ void __launch_bounds__(256, NB_CONV0_BLOCKS) conv0_mma_kernel(const f
             *reinterpret_cast<uint2*>(obase + (long long)(mt * 16 + 8) * CONV_DIM + np * 16) = v1;
         }
     }
+    } else {
+    // Channel-permuted tiles: the MMA's N axis is only a labelling of output channels, so column j of tile i of a group of NT
+    // tiles is made to carry channel 2 NT (j >> 1) + 2 i + (j & 1) of the group.  Lane q (which holds columns 2q, 2q+1 of every
+    // tile) then owns the 2 NT CONSECUTIVE channels 2 NT q .. 2 NT q + 2 NT - 1 of a row: one 8 / 16-byte store, no shuffles.
+    constexpr int GC = 8 * NT;  // channels per group
+    op_t* obase = out + (long long)(row_base + r) * CONV_DIM + warp * 64 + 2 * NT * q;
+#pragma unroll 1
+    for (int np = 0; np < 64 / GC; ++np) {
+        uint32_t bf[NT][2], bl[NT][2];
+        float sh[NT][2];
+        const int cb = warp * 64 + np * GC;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int cn = cb + 2 * NT * (r >> 1) + 2 * i + (r & 1);  // channel carried by column r of tile i
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cn) * 32);
+            bf[i][0] = __ldg(h + q);
+            bf[i][1] = __ldg(h + q + 4);
+            bl[i][0] = __ldg(h + 8 + q);
+            bl[i][1] = __ldg(h + 8 + q + 4);
+            const int cq = cb + 2 * NT * q + 2 * i;                   // channels of columns 2q, 2q+1 of tile i
+            sh[i][0] = __ldg(fold + ((long long)b * CONV_DIM + cq) * 12 + 10);
+            sh[i][1] = __ldg(fold + ((long long)b * CONV_DIM + cq + 1) * 12 + 10);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            uint32_t lo[NT], hi[NT];  // rows r / r + 8, channels 2 NT q + 2 i, + 1
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                float c[4] = {sh[i][0], sh[i][1], sh[i][0], sh[i][1]};
+                mma_f16_16816(c, a2[mt], bl[i][0], bl[i][1]);
+                mma_f16_16816(c, a1[mt], bf[i][0], bf[i][1]);
+#if NB_CONV0_GELU_H2
+                lo[i] = gelu_pair_h2(c[0], c[1]);
+                hi[i] = gelu_pair_h2(c[2], c[3]);
+#else
+                lo[i] = pack_op(gelu_act(c[0]), gelu_act(c[1]));
+                hi[i] = pack_op(gelu_act(c[2]), gelu_act(c[3]));
+#endif
+            }
+            const int row0 = mt * 16 + r, row1 = row0 + 8;
+            const bool ok0 = row0 < valid, ok1 = row1 < valid;
+            op_t* o0 = obase + (long long)(mt * 16) * CONV_DIM + np * GC;
+            op_t* o1 = o0 + 8 * CONV_DIM;
+            if constexpr (NT == 2) {
+                *reinterpret_cast<uint2*>(o0) = ok0 ? make_uint2(lo[0], lo[1]) : make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(o1) = ok1 ? make_uint2(hi[0], hi[1]) : make_uint2(0u, 0u);
+            } else {
+                *reinterpret_cast<uint4*>(o0) = ok0 ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(o1) = ok1 ? make_uint4(hi[0], hi[1], hi[2], hi[3]) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+    }
 }
 
 int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long row_begin,
@@ -375,7 +430,9 @@ int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, i
     const int blk0 = (int)(row_begin / C0_ROWS);
     if (blocks == 0) return 0;
     if (aux_out == nullptr && fold_h != nullptr && use_mma) {
-        conv0_mma_kernel<<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        if (use_mma == 2) conv0_mma_kernel<2><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        else if (use_mma == 3) conv0_mma_kernel<4><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        else conv0_mma_kernel<0><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
         NB_LAUNCHED();
         return 0;
     }

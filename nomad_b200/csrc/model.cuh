@@ -72,7 +72,7 @@ struct Weights {
     float* loss_head_wt; // loss head (LossNetLayers.embedding_layer), transposed [768][256]
     float* loss_head_w;  // [256][768] (backward)
     float* loss_head_b;
-    float* pos_scale_tmp;  // [128] g / ||v|| per tap, scratch of nomad_b200_refresh_weights (allocated on first use)
+    double* pos_scale_tmp;  // [128] g / ||v|| per tap, scratch of nomad_b200_refresh_weights (allocated on first use)
 };
 
 // fp32-class mode (precise.cu): a GEMM weight as hi + lo fp16 planes of w * 2^k (k per tensor, so that the lo plane

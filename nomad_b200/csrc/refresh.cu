@@ -5,6 +5,7 @@
 // training step would cost seconds.  Here it is a handful of bandwidth-bound kernels (~190 MB of fp32 read, ~0.5 GB written).
 // The conv feature encoder is frozen in the reference's configuration (`freeze_convnet: True`) and is not touched; the
 // fp32-class weight planes (precision_mode 1) are not rebuilt either: fine-tuning runs the fp16-operand path.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -43,19 +44,21 @@ __global__ void __launch_bounds__(256) rf_fold_kernel(const float* __restrict__ 
                                                       op_t* __restrict__ Wf, float* __restrict__ s, float* __restrict__ c, int row_off) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
-    float ss = 0.f, cs = 0.f;
+    double ss = 0.0, cs = 0.0;  // fp64 sums like the host build (api.cu: upload_folded), so both give the same fp32 vectors
     for (int k = lane; k < K; k += 32) {
-        const float w = W[(long long)n * K + k] * sc;
-        const op_t q = f2op(w * gamma[k]);
+        const float w = W[(long long)n * K + k];
+        const op_t q = f2op(__fmul_rn(__fmul_rn(w, sc), gamma[k]));
         Wf[(long long)(row_off + n) * K + k] = q;
-        ss += op2f(q);
-        cs = fmaf(w, beta[k], cs);
+        ss += (double)op2f(q);
+        cs += (double)w * (double)sc * (double)beta[k];
     }
-    ss = warp_sum(ss);
-    cs = warp_sum(cs);
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    }
     if (lane == 0) {
-        s[row_off + n] = ss;
-        c[row_off + n] = cs + b[n] * sc;
+        s[row_off + n] = (float)ss;
+        c[row_off + n] = (float)(cs + (double)b[n] * (double)sc);
     }
 }
 __global__ void rf_copy_scale_kernel(const float* __restrict__ src, int n, float scale, float* __restrict__ dst) {
@@ -68,7 +71,7 @@ __global__ void rf_transpose_f32_kernel(const float* __restrict__ src, int R, in
     if (i < R * C) dst[(long long)(i % C) * R + i / C] = src[i];
 }
 // positional conv: per-tap norms of weight_v over (out, in), then the two grouped layouts of w = g * v / ||v||
-__global__ void __launch_bounds__(256) rf_pos_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ scale) {
+__global__ void __launch_bounds__(256) rf_pos_norm_kernel(const float* __restrict__ v, const float* __restrict__ g, double* __restrict__ scale) {
     const int k = blockIdx.x;  // tap
     double a = 0.0;
     for (int i = threadIdx.x; i < 768 * POS_GC; i += 256) {
@@ -82,9 +85,9 @@ __global__ void __launch_bounds__(256) rf_pos_norm_kernel(const float* __restric
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) scale[k] = (float)((double)g[k] / sqrt(red[0]));
+    if (threadIdx.x == 0) scale[k] = (double)g[k] / sqrt(red[0]);
 }
-__global__ void __launch_bounds__(256) rf_pos_fold_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) rf_pos_fold_kernel(const float* __restrict__ v, const double* __restrict__ scale,
                                                           op_t* __restrict__ fw, op_t* __restrict__ bw) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // index into v: ((g*48 + n)*48 + c)*128 + k
     if (i >= (long long)768 * POS_GC * POS_K) return;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) rf_pos_fold_kernel(const float* __restric
     const int c = (int)((i / POS_K) % POS_GC);
     const int on = (int)(i / ((long long)POS_K * POS_GC));  // g * 48 + n
     const int g = on / POS_GC, n = on % POS_GC;
-    const op_t q = f2op(v[i] * scale[k]);
+    const op_t q = f2op((float)((double)v[i] * scale[k]));
     fw[(long long)on * (POS_K * POS_GC) + (long long)k * POS_GC + c] = q;
     bw[(long long)(g * POS_GC + c) * (POS_K * POS_GC) + (long long)(POS_K - 1 - k) * POS_GC + n] = q;
 }
@@ -140,12 +143,12 @@ extern "C" int nomad_b200_refresh_weights(nomad_b200_handle* hh, const nomad_b20
     RGET(pv, P + "encoder.pos_conv.0.weight_v", 768LL * POS_GC * POS_K); RGET(pg, P + "encoder.pos_conv.0.weight_g", POS_K);
     RGET(pbias, P + "encoder.pos_conv.0.bias", 768);
     {
-        float* scale = w.pos_scale_tmp;
+        double* scale = w.pos_scale_tmp;
         if (scale == nullptr) {
             void* d = nullptr;
-            NB_CUDA(cudaMalloc(&d, sizeof(float) * POS_K));
+            NB_CUDA(cudaMalloc(&d, sizeof(double) * POS_K));
             h->allocs.push_back(d);
-            scale = w.pos_scale_tmp = (float*)d;
+            scale = w.pos_scale_tmp = (double*)d;
         }
         rf_pos_norm_kernel<<<POS_K, 256, 0, st>>>(pv, pg, scale);
         NB_LAUNCHED();
@@ -201,5 +204,32 @@ extern "C" int nomad_b200_refresh_weights(nomad_b200_handle* hh, const nomad_b20
 #undef RGET
     NB_CHECK(!h->pw.built || h->precision == NOMAD_B200_PRECISION_FP16,
              "refresh_weights: the fp32-class weight planes are not rebuilt; switch the handle to precision_mode 0 for fine-tuning");
+    return 0;
+}
+
+// Test hook: copy one kernel-ready weight buffer to the host (synchronous).  which: "pos_w" | "pos_wt" | "l<k>.w_fc1_f" |
+// "l<k>.s_fc1" | "l<k>.c_fc1" | "l<k>.w_qkv_f" | "l<k>.s_qkv" | "l<k>.c_qkv" | "l<k>.w_qkv" | "l<k>.wt_fc2" | "head_wt"
+extern "C" int nomad_b200_debug_read_weight(nomad_b200_handle* hh, const char* which, void* dst_host, size_t bytes) {
+    NB_CHECK(hh && which && dst_host, "debug_read_weight: bad arguments");
+    Weights& w = hh->h.w;
+    const void* src = nullptr;
+    std::string s(which);
+    if (s == "pos_w") src = w.pos_w;
+    else if (s == "pos_wt") src = w.pos_wt;
+    else if (s == "head_wt") src = w.head_wt;
+    else if (s.size() > 2 && s[0] == 'l') {
+        const size_t dot = s.find('.');
+        NB_CHECK(dot != std::string::npos, "debug_read_weight: bad name %s", which);
+        const int l = atoi(s.substr(1, dot - 1).c_str());
+        NB_CHECK(l >= 0 && l < LAYERS, "debug_read_weight: bad layer in %s", which);
+        const std::string f = s.substr(dot + 1);
+        LayerWeights& L = w.layer[l];
+        if (f == "w_fc1_f") src = L.w_fc1_f; else if (f == "s_fc1") src = L.s_fc1; else if (f == "c_fc1") src = L.c_fc1;
+        else if (f == "w_qkv_f") src = L.w_qkv_f; else if (f == "s_qkv") src = L.s_qkv; else if (f == "c_qkv") src = L.c_qkv;
+        else if (f == "w_qkv") src = L.w_qkv; else if (f == "wt_fc2") src = L.wt_fc2;
+    }
+    NB_CHECK(src != nullptr, "debug_read_weight: unknown buffer %s", which);
+    NB_CUDA(cudaDeviceSynchronize());
+    NB_CUDA(cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }

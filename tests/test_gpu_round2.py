@@ -429,11 +429,28 @@ def test_device_weight_refresh_equals_a_fresh_handle(state_dict):
     g = torch.Generator().manual_seed(77)
     sd2 = {k: (v + 0.01 * v.abs().mean() * torch.randn(v.shape, generator=g) if "feature_extractor" not in k else v.clone())
            for k, v in state_dict.items()}
+    import ctypes as C
+    from nomad_b200 import _lib
     a = Engine(state_dict, 0)
     b = Engine(sd2, 0)
     waves = [0.1 * torch.randn(n, generator=g) for n in (16000, 20481, 4000)]
     before = a.embed(waves).clone()
     a.refresh_weights({k: v.cuda().contiguous() for k, v in sd2.items()})
+
+    def read(e, name, n, dt):
+        buf = np.empty(n, dt)
+        _lib.check(e.lib.nomad_b200_debug_read_weight(e.handle, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), name)
+        return buf
+    # the kernel-ready buffers themselves: same bits as the host build (same fp64 fold arithmetic on both sides)
+    for name, n, dt in (("pos_w", 16 * 48 * 6144, np.uint16), ("pos_wt", 16 * 48 * 6144, np.uint16),
+                        ("l3.w_fc1_f", 3072 * 768, np.uint16), ("l3.s_fc1", 3072, np.float32), ("l3.c_fc1", 3072, np.float32),
+                        ("l3.w_qkv_f", 2304 * 768, np.uint16), ("l3.s_qkv", 2304, np.float32), ("l3.c_qkv", 2304, np.float32),
+                        ("l0.w_qkv", 2304 * 768, np.uint16), ("l11.wt_fc2", 3072 * 768, np.uint16), ("head_wt", 768 * 256, np.float32)):
+        x, y = read(a, name, n, dt), read(b, name, n, dt)
+        if dt is np.float32:   # fp64 sums in a different order: equal up to the final rounding
+            assert np.abs(x.astype(np.float64) - y).max() <= 2.4e-7 * max(1.0, np.abs(y).max()), name
+        else:
+            assert np.array_equal(x, y), (name, int((x != y).sum()))
     ea, eb = a.embed(waves), b.embed(waves)
     assert float((before - eb).abs().max()) > 1e-4          # the weights really changed
     assert float((ea - eb).abs().max()) <= 2e-6              # fold sums are fp32 on the device, fp64 on the host
