@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                     const AttnFaArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space (LDS / STS, not generic LD / ST)
     uint8_t* sQ = smem;
     uint8_t* sRing = smem + FA_OFF_RING;
     uint8_t* sP = smem + FA_OFF_P;

@@ -42,6 +42,8 @@ struct GemmArgs {
     // B operand's K origin moves by b_kshift0 + batch * b_kshift_step elements (negative / past-the-end columns read as
     // zero): batch = tap of a correlation sum_k A[m, k] B[n, k + tap] (the positional conv's weight gradient)
     int shared_ab, b_kshift0, b_kshift_step, b_mod;  // B batch coordinate = batch % b_mod, K shift = b_kshift0 + (batch / b_mod) * step
+    int resid_tma;      // residual epilogues (prefetch variant): fetch the residual tiles with TMA instead of cp.async
+    int resid_l2pf;     // residual epilogues: L2-prefetch the next tile's slice of the fp32 residual stream (tiles ahead, 0 = off)
     unsigned sleep_ns;  // back-off of the waiting TMA / MMA role threads (0 = spin); they share schedulers with epilogue warps
     GemmEpilogue epi;
 };
@@ -70,6 +72,12 @@ struct RowCtx {
     float* rbuf;
     bool rhave;
     const float* rnext;
+    // the same prefetch as ONE TMA tile load per chunk (box 32 x 32 fp32 in the staging swizzle, completion on this warp's own
+    // mbarrier) instead of 8 cp.async per lane: nullptr = cp.async
+    const CUtensorMap* tm_r;
+    uint64_t* rbar;
+    uint32_t rphase;
+    const float* rbase;  // origin of the residual matrix (tile coordinates = (rnext - rbase) / ldr, % ldr)
     // Column vectors of this warp's column range (bias or c | s or gamma | beta), staged in shared memory once per
     // tile by epilogue_stage_vectors: the chunk loop then reads them with broadcast LDS instead of one L2 round
     // trip per chunk (the kernel's 200+ KB of shared memory leave almost no L1).  nullptr = read global memory.
@@ -87,6 +95,16 @@ struct RowCtx {
     int stage_bytes;           // 4096 or 6144 per warp
     int flip;                  // alternates the 16-bit slot when the area has no room for fp32 + 16-bit side by side
 };
+// residual tile request through TMA: the warp has finished reading rbuf (the caller's __syncwarp), lane 0 arms the barrier
+__device__ __forceinline__ void resid_tma_issue(const CUtensorMap* map, uint64_t* bar, float* rbuf, const float* src,
+                                                const float* base, long long ld, int lane) {
+    if (lane == 0) {
+        const long long off = src - base;
+        const int row = (int)(off / ld), col = (int)(off - (long long)row * ld);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d_cta(rbuf, map, bar, col, row);
+    }
+}
 // wait until the slots in `mask` are free again (warp-uniform), then mark them as about to be in flight
 __device__ __forceinline__ void ts_acquire(RowCtx& rc, uint32_t mask, int lane) {
     if (rc.pending & mask) {
@@ -166,7 +184,10 @@ __device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& e, fl
 }
 
 // FULL: all 32 rows of the warp are valid and the chunk has all 32 columns (compile-time: no predicates)
-template <bool FULL, int EF, bool PREC = false, bool TS = false>
+// SV / RP (flag-specialised pair kernels, whose launcher guarantees N % 256 == 0 and one batch): the column vectors are
+// always staged / every FULL chunk's residual tile was prefetched -- as compile-time facts, so the global-load twins of
+// those reads are not even issued predicated-off (they were 72 of ~860 issue slots per chunk of a latency-bound warp).
+template <bool FULL, int EF, bool PREC = false, bool TS = false, bool SV = false, bool RP = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)[32], long long row, bool row_ok,
                                                int rows_valid, int col0, int ncols, int b, float* stage, int lane,
                                                RowCtx& rc) {
@@ -183,8 +204,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const float4 t = (FULL && rc.vec) ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j)
-                                                  : __ldg(bp + j);
+                const float4 t = (FULL && (SV || rc.vec)) ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j)
+                                                          : __ldg(bp + j);
                 v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
         }
@@ -196,7 +217,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const bool sv = FULL && rc.vec != nullptr;
+                const bool sv = FULL && (SV || rc.vec != nullptr);
                 const float4 a = sv ? *reinterpret_cast<const float4*>(rc.vec + rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
                                     : __ldg(sp + j);
                 const float4 c = sv ? *reinterpret_cast<const float4*>(rc.vec + (col0 - rc.vec_col0) + 4 * j) : __ldg(cp + j);
@@ -255,8 +276,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
             }
         }
     }
-    const bool rpf = FULL && rc.rhave;  // warp-uniform
-    if (rpf) stage_fill_wait();
+    const bool rpf = FULL && (RP || rc.rhave);  // warp-uniform
+    if (rpf) {
+        if (rc.tm_r != nullptr) {
+            mbar_wait(rc.rbar, rc.rphase);
+            rc.rphase ^= 1;
+        } else {
+            stage_fill_wait();
+        }
+    }
     if ((FULL || row_ok) && (flags & EPI_RESID)) {
         const float4* rp =
             reinterpret_cast<const float4*>(e.resid + row * e.ldr + col0 + (long long)b * e.resid_bstride);
@@ -278,7 +306,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (FULL || j * 4 < ncols) {
-                const bool sv = FULL && rc.vec != nullptr;
+                const bool sv = FULL && (SV || rc.vec != nullptr);
                 const float4 t = rpf ? stage_row_f32(rc.rbuf, lane, j) : __ldg(rp + j);
                 const float4 g = sv ? *reinterpret_cast<const float4*>(rc.vec + rc.vec_stride + (col0 - rc.vec_col0) + 4 * j)
                                     : __ldg(gp + j);
@@ -294,7 +322,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, float (&v)
     if (rc.rbuf != nullptr) {  // warp-uniform
         if (rpf) __syncwarp();  // every lane has read its row
         rc.rhave = rc.rnext != nullptr;
-        if (rc.rhave) stage_fill_f32_async(rc.rbuf, rc.rnext, e.ldr, lane);
+        if (rc.rhave) {
+            if (rc.tm_r != nullptr) resid_tma_issue(rc.tm_r, rc.rbar, rc.rbuf, rc.rnext, rc.rbase, e.ldr, lane);
+            else stage_fill_f32_async(rc.rbuf, rc.rnext, e.ldr, lane);
+        }
     }
     if (flags & EPI_STATS_OUT) {  // two-pass statistics of this chunk, merged pairwise into 64-column partials
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -468,12 +499,15 @@ __device__ __forceinline__ double cdist_chunk(const GemmEpilogue& e, float (&v)[
 // they are added here in IEEE fp32.
 struct StoreMaps {
     const CUtensorMap *f, *h, *a;
+    const CUtensorMap* r;  // residual tile loads through TMA (nullptr = cp.async)
+    uint64_t* rbar;
+    uint32_t* rphase;      // carried across the tiles of a warp
     int stage_bytes;
     uint32_t* pending;  // carried across the tiles of a warp
     int* flip;
 };
 
-template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false, int PACC = 0, bool TS = false>
+template <int CHUNKS, bool PAIR, bool CDIST, int EF, bool PREC = false, int PACC = 0, bool TS = false, bool SV = false, bool RP = false>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t taddr, long long row, int col_first,
                                               int ccol_first, int b, uint64_t* tmem_empty_bar, int lane, float* stage,
                                               float2 row_st, float* rbuf, bool& rhave, const float* next_tile_src,
@@ -493,6 +527,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
     rc.vec_stride = vec_stride;
     rc.vec_col0 = col_first;
     rc.tm_f = rc.tm_h = rc.tm_a = nullptr;
+    rc.tm_r = nullptr; rc.rbar = nullptr; rc.rphase = 0; rc.rbase = args.epi.resid;
+    if (sm != nullptr && sm->r != nullptr) { rc.tm_r = sm->r; rc.rbar = sm->rbar; rc.rphase = *sm->rphase; }
     rc.pending = 0;
     rc.stage_bytes = 4096;
     rc.flip = 0;
@@ -542,11 +578,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (CDIST) row_sum += cdist_chunk(args.epi, v, row, row_ok, rows_valid, col0, ncols, stage, lane, TS ? &rc : nullptr);
-            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF, PREC, TS>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
+            else if (rows_valid == 32 && ncols == 32) epilogue_chunk<true, EF, PREC, TS, SV, RP>(args.epi, v, row, true, 32, col0, 32, b, stage, lane, rc);
             else epilogue_chunk<false, EF, PREC, TS>(args.epi, v, row, row_ok, rows_valid, col0, ncols, b, stage, lane, rc);
         }
     }
     rhave = rc.rhave;
+    if (sm != nullptr && sm->r != nullptr) *sm->rphase = rc.rphase;
     if (TS && sm != nullptr) {
         *sm->pending = rc.pending;
         *sm->flip = rc.flip;
@@ -565,7 +602,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using Cfg = TileCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space (LDS / STS, not generic LD / ST)
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -744,14 +781,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutH,
-                    const __grid_constant__ CUtensorMap tmAux, const GemmArgs args) {
+                    const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmResid, const GemmArgs args) {
     using Cfg = Pair256;
     constexpr int STAGES = Cfg::stages(NEW, RPF);
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space (LDS / STS, not generic LD / ST)
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
     constexpr int SB = Cfg::stage_bytes(NEW, CDIST);  // staging bytes per epilogue warp
+    // flag-specialised instantiations are only launched for N % 256 == 0, one batch (launch_pair): vectors always staged
+    constexpr bool SPEC_SV = !CDIST && EF >= 0 && (EF & (EPI_BIAS | EPI_LN_FOLD | EPI_RESID_LN)) != 0;
     float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB);
     float* vec_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF) +
@@ -759,7 +798,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* resid_bar = tmem_empty + 2;  // [NEW] one per epilogue warp (residual tiles through TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + NEW);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -783,6 +823,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 2 * NEW);  // epilogue warps of BOTH CTAs arrive on the leader's
         }
+        for (int s = 0; s < NEW; ++s) mbar_init(&resid_bar[s], 1);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -880,11 +921,16 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         smaps.stage_bytes = SB;
         smaps.pending = &ts_pending;
         smaps.flip = &ts_flip;
+        uint32_t rphase = 0;
+        smaps.r = (want_pf && args.resid_tma) ? &tmResid : nullptr;
+        smaps.rbar = &resid_bar[ew];
+        smaps.rphase = &rphase;
         bool rhave = false;
         if (want_pf) {
             const float* src = tile_src(pair_id);
             if (src != nullptr) {
-                stage_fill_f32_async(rbuf, src, args.epi.ldr, lane);
+                if (smaps.r != nullptr) resid_tma_issue(smaps.r, smaps.rbar, rbuf, src, args.epi.resid, args.epi.ldr, lane);
+                else stage_fill_f32_async(rbuf, src, args.epi.ldr, lane);
                 rhave = true;
             }
         }
@@ -897,10 +943,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t aphase = (it >> 1) & 1;
             const long long row = (long long)m_blk * 256 + rank * BM + q * 32 + lane;
             const float2 row_st = CDIST ? make_float2(0.f, 1.f) : epilogue_row_stats<EF>(args, row);
-            if (!CDIST && !want_pf && (eflags & (EPI_RESID | EPI_RESID_LN)) && tile + num_pairs < num_tiles) {
-                // no prefetch buffer (16-warp variant): at least pull the NEXT tile's slice of the fp32 residual
-                // stream into L2 a whole mainloop ahead of its use
-                const int nt = tile + num_pairs;
+            if (!CDIST && (!want_pf || args.resid_l2pf > 0) && (eflags & (EPI_RESID | EPI_RESID_LN)) &&
+                tile + (want_pf ? args.resid_l2pf : 1) * num_pairs < num_tiles) {
+                // pull a LATER tile's slice of the fp32 residual stream into L2 a whole tile ahead of its use: the one-chunk
+                // shared-memory prefetch of a warp keeps only 4 KB in flight, i.e. 32 KB per SM -- at the ~3 k cycles of a
+                // loaded HBM round trip that is 2.6 TB/s for the whole GPU (measured: +65 us for the 157 MB residual of the
+                // out-projection, profiles/r02_outproj_knockout.log); from L2 the same fills return in a fraction of that
+                const int nt = tile + (want_pf ? args.resid_l2pf : 1) * num_pairs;
                 const int n2 = nt % args.n_tiles, m2 = (nt / args.n_tiles) % args.m_tiles;
                 const long long r2 = (long long)m2 * 256 + rank * BM + q * 32 + lane;
                 const int c2 = n2 * BN + h * HALF;
@@ -917,7 +966,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<HALF / 32, true, CDIST, EF, PREC, 0, TS>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+            epilogue_tile<HALF / 32, true, CDIST, EF, PREC, 0, TS, SPEC_SV, SPEC_SV && RPF && (EF & (EPI_RESID | EPI_RESID_LN)) != 0>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * (SB / 4),
                                            row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h, &smaps);
         }
@@ -1186,7 +1235,8 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
     int pairs = device_sm_count() / 2;
     if (tiles < pairs) pairs = (int)tiles;
     NB_TRY(prof_begin(st, 2.0 * args.M * args.N * args.K * args.batch));
-    CUtensorMap tmF = tmA, tmH = tmA, tmX = tmA;  // placeholders when an output is absent
+    CUtensorMap tmF = tmA, tmH = tmA, tmX = tmA, tmR = tmA;  // placeholders when an output is absent
+    if (RPF && args.resid_tma) NB_TRY(make_store_map(&tmR, args.epi.resid, true, args.M, args.N, args.epi.ldr));
     if (TS) {
         const GemmEpilogue& e = args.epi;
         if ((e.flags & (EPI_OUT_F32 | EPI_CDIST)) && e.out_f) NB_TRY(make_store_map(&tmF, e.out_f, true, args.M, args.N, e.ldo));
@@ -1206,9 +1256,9 @@ static int launch_pair_impl(cudaStream_t st, const GemmOperand& A, const GemmOpe
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        NB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS>, tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args));
+        NB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS>, tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, tmR, args));
     } else {
-        gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, args);
+        gemm_tc_pair_kernel<NEW, CDIST, RPF, EF, PREC, TS><<<2 * pairs, 128 + 32 * NEW, SMEM, st>>>(tmA, tmB, tmA2, tmB2, tmF, tmH, tmX, tmR, args);
     }
     NB_LAUNCHED();
     NB_TRY(prof_end(st));
@@ -1228,7 +1278,8 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     const bool heavy = args.K <= 1024 && ((fl & (EPI_GELU | EPI_SAVE_DGELU)) != 0 ||
                                           ((fl & (EPI_RESID | EPI_RESID_LN)) != 0 && !(fl & EPI_STATS_OUT)));
     // hot flag combinations of the scoring path run flag-specialised instantiations (NOMAD_B200_EPI_SPEC=0: generic)
-    static const int spec = getenv("NOMAD_B200_EPI_SPEC") ? atoi(getenv("NOMAD_B200_EPI_SPEC")) : 1;
+    static const int spec_env = getenv("NOMAD_B200_EPI_SPEC") ? atoi(getenv("NOMAD_B200_EPI_SPEC")) : 1;
+    const bool spec = spec_env && args.N % Pair256::BN == 0 && args.batch == 1;  // what SPEC_SV in the kernel relies on
     constexpr int F_FC1 = EPI_LN_FOLD | EPI_GELU | EPI_OUT_H16;
     constexpr int F_QKV = EPI_LN_FOLD | EPI_OUT_H16;
     constexpr int F_CONV = EPI_GELU | EPI_OUT_H16;
@@ -1288,6 +1339,11 @@ int gemm_h16(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M,
     args.shared_ab = g_corr_on; args.b_kshift0 = g_corr_shift0; args.b_kshift_step = g_corr_step; args.b_mod = g_corr_mod;
     static const unsigned sleep_ns = getenv("NOMAD_B200_GEMM_SLEEP") ? (unsigned)atoi(getenv("NOMAD_B200_GEMM_SLEEP")) : 0u;
     args.sleep_ns = sleep_ns;
+    static const int resid_l2pf = getenv("NOMAD_B200_RESID_L2PF") ? atoi(getenv("NOMAD_B200_RESID_L2PF")) : 0;
+    args.resid_l2pf = resid_l2pf;
+    static const int resid_tma = getenv("NOMAD_B200_RESID_TMA") ? atoi(getenv("NOMAD_B200_RESID_TMA")) : 0;
+    args.resid_tma = (resid_tma && (epi.flags & (EPI_RESID | EPI_RESID_LN)) && epi.resid != nullptr && batch == 1 &&
+                      ((uintptr_t)epi.resid & 15) == 0 && (epi.ldr * 4) % 16 == 0) ? 1 : 0;
     NB_CHECK(B.k_wrap == 0, "only the A operand may use wrapped K");
     if (epi.flags & EPI_PRECISE) {
         NB_CHECK(impl == 0 && A.lo != nullptr && B.lo != nullptr && epi.acc_scale > 0.f, "EPI_PRECISE needs hi + lo operand planes and a scale");

@@ -75,7 +75,7 @@ __device__ __forceinline__ void umma_f16_parts(uint32_t tmem_d, uint32_t a_lo, u
 __global__ void __launch_bounds__(PC_THREADS, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap tmSlab, const __grid_constant__ CUtensorMap tmW, const PosConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps the address space (LDS / STS, not generic LD / ST)
     uint8_t* slab[2] = {smem, smem + PC_SLAB_BYTES};
     uint8_t* bst = smem + 2 * PC_SLAB_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(bst + PC_BSTAGES * PC_BSTAGE_BYTES);

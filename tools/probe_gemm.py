@@ -32,6 +32,14 @@ CASES = {
     "bigconv": (409600, 512, 1536, 1024, 0, 1, 2 | 16),
     "bigout": (51200, 768, 768, 0, 0, 1, 1 | 4 | 8),
     "bigconv2": (204800, 512, 1536, 1024, 0, 1, 2 | 16),
+    # epilogue knock-outs on the out-projection shape (which part of the residual epilogue costs what)
+    "out_h": (51200, 768, 768, 0, 0, 1, 16),
+    "out_bh": (51200, 768, 768, 0, 0, 1, 1 | 16),
+    "out_f": (51200, 768, 768, 0, 0, 1, 8),
+    "out_fh": (51200, 768, 768, 0, 0, 1, 8 | 16),
+    "out_rf": (51200, 768, 768, 0, 0, 1, 4 | 8),
+    "out_rfh": (51200, 768, 768, 0, 0, 1, 1 | 4 | 8 | 16),
+    "out_rh": (51200, 768, 768, 0, 0, 1, 1 | 4 | 16),
 }
 
 
