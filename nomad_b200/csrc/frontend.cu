@@ -423,14 +423,108 @@ __global__ void __launch_bounds__(256, NB_CONV0_BLOCKS) conv0_mma_kernel(const f
     }
 }
 
+// Variant 4: the A fragments (hi / lo split samples in mma layout) depend on (row tile, lane) only, not on the warp's channel
+// range -- so warps 0..3 build one row tile each ONCE per block into shared memory (4 KB) instead of all 8 warps building all four
+// (12 % of the kernel's instructions), and every warp reads the 8 registers of the tile it is working on with two LDS.128.
+// That frees 24 registers: 64 per thread, FOUR blocks per SM (32 warps instead of 24) for a kernel bound by instruction latency.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) conv0_mma_s_kernel(const float* __restrict__ wav, const UttMeta* __restrict__ meta,
+                                                             int B, int blk0, const float* __restrict__ fold,
+                                                             const op_t* __restrict__ fold_h, op_t* __restrict__ out) {
+    const int blk = blk0 + blockIdx.x;
+    const int row_base = blk * C0_ROWS;
+    const int b = find_utt_by_frame(meta, B, blk);
+    const UttMeta m = meta[b];
+    const int t_base = row_base - m.row0;
+    __shared__ float xs[C0_ROWS * 5 + 16];
+    __shared__ uint4 frag[4][2][32];  // [row tile][k-step][lane]
+    const float* x = wav + m.wav_off;
+    for (int i = threadIdx.x; i < C0_ROWS * 5 + 16; i += blockDim.x) {
+        const long long s = (long long)t_base * 5 + i;
+        xs[i] = (s < m.n) ? __ldg(x + s) : 0.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, q = lane & 3;
+    __syncthreads();
+    const int valid = m.T0 - t_base;
+    if (warp < 4) {
+        const int mt = warp;
+        uint32_t a1[4], a2[4];
+        const int ib[2] = {5 * (mt * 16 + r), 5 * (mt * 16 + r) + 40};  // first sample of rows r and r + 8
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float* x = xs + ib[k];
+            a1[k] = pack_op(x[2 * q], x[2 * q + 1]);
+            {
+                const int o = q == 0 ? 8 : 2 * q - 2;
+                const float x0 = x[o], x1 = x[o + 1];
+                const uint32_t hh = pack_op(x0, x1);
+                const float2 hf = unpack_op(hh);
+                a1[2 + k] = q == 0 ? hh : pack_op(x0 - hf.x, x1 - hf.y);
+            }
+            {
+                const int o = q < 2 ? 6 + 2 * q : 2 * q - 4;
+                const float x0 = x[o], x1 = x[o + 1];
+                const uint32_t hh = pack_op(x0, x1);
+                const float2 hf = unpack_op(hh);
+                a2[k] = q < 2 ? pack_op(x0 - hf.x, x1 - hf.y) : hh;
+            }
+            a2[2 + k] = pack_op(x[2 * q + 4], x[2 * q + 5]);
+        }
+        frag[mt][0][lane] = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+        frag[mt][1][lane] = make_uint4(a2[0], a2[1], a2[2], a2[3]);
+    }
+    __syncthreads();
+    constexpr int NT = 2, GC = 8 * NT;
+    op_t* obase = out + (long long)(row_base + r) * CONV_DIM + warp * 64 + 2 * NT * q;
+#pragma unroll 1
+    for (int np = 0; np < 64 / GC; ++np) {
+        uint32_t bf[NT][2], bl[NT][2];
+        float sh[NT][2];
+        const int cb = warp * 64 + np * GC;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int cn = cb + 2 * NT * (r >> 1) + 2 * i + (r & 1);  // channel carried by column r of tile i
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(fold_h + ((long long)b * CONV_DIM + cn) * 32);
+            bf[i][0] = __ldg(h + q);
+            bf[i][1] = __ldg(h + q + 4);
+            bl[i][0] = __ldg(h + 8 + q);
+            bl[i][1] = __ldg(h + 8 + q + 4);
+            const int cq = cb + 2 * NT * q + 2 * i;
+            sh[i][0] = __ldg(fold + ((long long)b * CONV_DIM + cq) * 12 + 10);
+            sh[i][1] = __ldg(fold + ((long long)b * CONV_DIM + cq + 1) * 12 + 10);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const uint4 f1 = frag[mt][0][lane], f2 = frag[mt][1][lane];
+            const uint32_t a1[4] = {f1.x, f1.y, f1.z, f1.w}, a2[4] = {f2.x, f2.y, f2.z, f2.w};
+            uint32_t lo[NT], hi[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                float c[4] = {sh[i][0], sh[i][1], sh[i][0], sh[i][1]};
+                mma_f16_16816(c, a2, bl[i][0], bl[i][1]);
+                mma_f16_16816(c, a1, bf[i][0], bf[i][1]);
+                lo[i] = gelu_pair_h2(c[0], c[1]);
+                hi[i] = gelu_pair_h2(c[2], c[3]);
+            }
+            const int row0 = mt * 16 + r, row1 = row0 + 8;
+            op_t* o0 = obase + (long long)(mt * 16) * CONV_DIM + np * GC;
+            *reinterpret_cast<uint2*>(o0) = row0 < valid ? make_uint2(lo[0], lo[1]) : make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(o0 + 8 * CONV_DIM) = row1 < valid ? make_uint2(hi[0], hi[1]) : make_uint2(0u, 0u);
+        }
+    }
+}
+
 int launch_conv0_apply(cudaStream_t st, const float* wav, const UttMeta* meta, int B, long long row_begin,
                        long long row_end, const float* fold, const op_t* fold_h, op_t* out, op_t* aux_out) {
-    static const int use_mma = getenv("NOMAD_B200_CONV0_MMA") ? atoi(getenv("NOMAD_B200_CONV0_MMA")) : 1;
+    static const int use_mma = getenv("NOMAD_B200_CONV0_MMA") ? atoi(getenv("NOMAD_B200_CONV0_MMA")) : 4;  // 0 SIMT; 1 row-major tiles + shuffles 1.36-1.42 ms; 2 / 3 channel-permuted 1.27 / 1.45; 4 / 5 = 2 + shared A fragments at 4 / 3 blocks per SM 1.16 / 1.29
     const unsigned blocks = (unsigned)((row_end - row_begin) / C0_ROWS);
     const int blk0 = (int)(row_begin / C0_ROWS);
     if (blocks == 0) return 0;
     if (aux_out == nullptr && fold_h != nullptr && use_mma) {
-        if (use_mma == 2) conv0_mma_kernel<2><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        if (use_mma == 4) conv0_mma_s_kernel<4><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        else if (use_mma == 5) conv0_mma_s_kernel<3><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
+        else if (use_mma == 2) conv0_mma_kernel<2><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
         else if (use_mma == 3) conv0_mma_kernel<4><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
         else conv0_mma_kernel<0><<<blocks, 256, 0, st>>>(wav, meta, B, blk0, fold, fold_h, out);
         NB_LAUNCHED();
