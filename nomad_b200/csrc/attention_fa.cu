@@ -1,9 +1,9 @@
 // Attention core softmax(Q K^T) V on tcgen05 for utterances of ANY length (non-causal, keys >= T masked).
 // q is already scaled by head_dim^-0.5 (folded into the QKV weights).
 //
-// Work item = (utterance, head, 128-query tile).  A persistent CTA (192 threads, THREE CTAs per SM: 64 KB of
-// shared memory, 128 TMEM columns, <= 112 registers) walks a host-built item list (longest utterances first)
-// and streams 64-key tiles through a 4-stage TMA ring:
+// Work item = (utterance, head, 128-query tile).  A persistent CTA (192 threads, FOUR CTAs per SM: 49 KB of
+// shared memory, 128 TMEM columns -- all 512 of the SM --, 80 registers) walks a host-built item list (longest
+// utterances first) and streams 64-key tiles through a 2-stage TMA ring:
 //   warp 0 (one lane)  TMA producer: Q tile (16 KB), then K_0, V_0, K_1, V_1, ... (8 KB boxes, 128B swizzle)
 //   warp 1 (one lane)  MMA issuer:   S = Q K_j^T      tcgen05.mma M=128 N=64 K=64  -> TMEM columns [0, 64)
 //                                    O (+)= P_j V_j   tcgen05.mma M=128 N=64 K<=64 -> TMEM columns [64, 128)
@@ -16,7 +16,8 @@
 // bound by instruction issue in the softmax warps (ncu: ~9 instructions per score, IPC ~0.45 with two warps
 // per scheduler), not by the MMAs or their latency -- double/triple-buffered S, lazy rescaling and deferred
 // epilogues were all measured and bought nothing (profiles/r01_attention_notes.md) -- so the design goes for
-// occupancy instead: small tiles let three CTAs (12 softmax warps) share an SM and fill each other's gaps.
+// occupancy instead: small tiles let four CTAs (16 softmax warps) share an SM and fill each other's gaps
+// (round 2: three -> four CTAs by halving the K/V ring, which was measured not to matter: -4..7 %).
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -29,7 +30,13 @@ namespace nb {
 static constexpr int FA_THREADS = 192;
 static constexpr int FA_BK = 64;                                  // keys per tile
 static constexpr int FA_CHUNKS = FA_BK / 32;
-static constexpr int FA_RING = 4;
+#ifndef NB_FA_RING
+#define NB_FA_RING 2   // K, V stages of 8 KB: 2 leave room for a fourth CTA per SM (4 and 2 measured equal at 3 CTAs)
+#endif
+#ifndef NB_FA_CTAS
+#define NB_FA_CTAS 4   // 80 registers (48 B of spills), 4 x 128 TMEM columns: 1.57-1.60 -> 1.45-1.53 ms per 12 layers
+#endif
+static constexpr int FA_RING = NB_FA_RING;
 static constexpr int FA_Q_BYTES = 16384;                          // 128 rows x 128 B
 static constexpr int FA_TILE_BYTES = FA_BK * 128;                 // K or V tile: FA_BK rows x 128 B
 static constexpr int FA_P_BYTES = (FA_BK / 64) * 16384;           // P = 64-key blocks of 128 rows x 128 B
@@ -39,7 +46,7 @@ static constexpr int FA_OFF_BAR = FA_OFF_P + FA_P_BYTES;
 static constexpr int FA_SMEM = FA_OFF_BAR + 128 + 1024;           // barriers + alignment slack
 static constexpr uint32_t FA_TMEM_COLS = 128;
 static constexpr uint32_t FA_O_COL = FA_BK;
-static constexpr int FA_CTAS_PER_SM = 3;
+static constexpr int FA_CTAS_PER_SM = NB_FA_CTAS;
 
 // One (utterance, query tile) of the work list; every entry stands for HEADS work items.
 struct FaEntry {
