@@ -347,8 +347,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// NB_MBAR_HINT_NS > 0: try_wait carries a suspend-time hint, so a waiting thread sleeps in hardware until the phase completes
+// (or the hint runs out) instead of re-issuing the test: the spin loops of the attention kernel's softmax warps were HALF of
+// all instructions it issued (profiles/r02b_ncu_misc: BRA + SYNCS + YIELD = 10 of 22 thread instructions per score).
+#ifndef NB_MBAR_HINT_NS
+#define NB_MBAR_HINT_NS 20000   // measured (alternating builds, one box): step 16.40-16.54 -> 16.16-16.17 ms, FC1 228-238 -> 214 us, QKV 171 -> 163 us
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if NB_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)NB_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
@@ -356,6 +371,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
