@@ -62,8 +62,8 @@ FALLBACK_HBM_GBS = 6500.0
 # dram__bytes_read.sum + dram__bytes_write.sum per tensor-core GEMM launch, averaged over the GEMM launches of one
 # step, from the ncu pass named in TRAFFIC_SOURCE (not measured in this run; the algorithmic operand + result bytes of
 # those launches are 33.7 GB per step)
-GEMM_DRAM_TRAFFIC_BYTES = 563.5e6
-TRAFFIC_SOURCE = "ncu profile profiles/r02b_gemm_dram.csv (31.0 GB over the 55 GEMM launches of one step)"
+GEMM_DRAM_TRAFFIC_BYTES = 559.7e6
+TRAFFIC_SOURCE = "ncu profile profiles/r02c_gemm_dram.csv (30.8 GB over the 55 GEMM launches of one step)"
 
 
 def log(*a):
