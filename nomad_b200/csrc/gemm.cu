@@ -790,7 +790,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
     constexpr int SB = Cfg::stage_bytes(NEW, CDIST);  // staging bytes per epilogue warp
     // flag-specialised instantiations are only launched for N % 256 == 0, one batch (launch_pair): vectors always staged
-    constexpr bool SPEC_SV = !CDIST && EF >= 0 && (EF & (EPI_BIAS | EPI_LN_FOLD | EPI_RESID_LN)) != 0;
+    constexpr bool SPEC = !CDIST && EF >= 0;
+    constexpr bool SPEC_SV = SPEC && (EF & (EPI_BIAS | EPI_LN_FOLD | EPI_RESID_LN)) != 0;
     float* resid_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB);
     float* vec_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + NEW * SB + Cfg::resid_bytes(NEW, RPF) +
@@ -966,7 +967,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epilogue_tile<HALF / 32, true, CDIST, EF, PREC, 0, TS, SPEC_SV, SPEC_SV && RPF && (EF & (EPI_RESID | EPI_RESID_LN)) != 0>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
+            epilogue_tile<HALF / 32, true, CDIST, EF, PREC, 0, TS, SPEC_SV, SPEC && RPF && (EF & (EPI_RESID | EPI_RESID_LN)) != 0>(args, tmem_base + (uint32_t)(as * 256 + h * HALF) + ((uint32_t)(q * 32) << 16), row,
                                            n_blk * BN + h * HALF, h * HALF, b, &tmem_empty[as], lane, epi_stage + ew * (SB / 4),
                                            row_st, rbuf, rhave, next_src, vec, HALF, n_blk * (NEW / 4) + h, &smaps);
         }
@@ -1289,7 +1290,13 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     constexpr int F_CONV_SAVE = EPI_GELU | EPI_OUT_H16 | EPI_SAVE_DGELU;
     constexpr int F_LIN_H16 = EPI_BIAS | EPI_OUT_H16;
     constexpr int F_RES_PLAIN = EPI_BIAS | EPI_RESID_LN | EPI_OUT_F32;
+    constexpr int F_BRES = EPI_BIAS | EPI_RESID | EPI_OUT_F32;   // loss forward: out-proj / FC2 (explicit LayerNorm kernels follow)
+    constexpr int F_DG_RES = EPI_RESID | EPI_OUT_F32;            // dgrad + residual branch
+    constexpr int F_DG_AUX = EPI_MUL_AUX | EPI_OUT_H16;          // dgrad through GELU (x gelu')
+    constexpr int F_H16 = EPI_OUT_H16;                           // plain dgrad
     if (epi16 == 2 || (epi16 == 1 && heavy)) {
+        if (spec && fl == F_BRES) return launch_pair_impl<16, false, false, F_BRES>(st, A, B, args);
+        if (spec && fl == F_RES_PLAIN) return launch_pair_impl<16, false, false, F_RES_PLAIN>(st, A, B, args);
         if (spec && fl == F_FC1) return launch_pair_impl<16, false, false, F_FC1>(st, A, B, args);
         if (spec && fl == F_CONV) return launch_pair_impl<16, false, false, F_CONV>(st, A, B, args);
         if (spec && fl == F_FC1_SAVE) return launch_pair_impl<16, false, false, F_FC1_SAVE>(st, A, B, args);
@@ -1302,12 +1309,16 @@ static int launch_pair(cudaStream_t st, const GemmOperand& A, const GemmOperand&
     if (rpf && (fl & (EPI_RESID | EPI_RESID_LN)) != 0 && args.batch == 1) {
         if (spec && fl == F_RES) return launch_pair_impl<8, false, true, F_RES>(st, A, B, args);
         if (spec && fl == F_RES_PLAIN) return launch_pair_impl<8, false, true, F_RES_PLAIN>(st, A, B, args);
+        if (spec && fl == F_BRES) return launch_pair_impl<8, false, true, F_BRES>(st, A, B, args);
+        if (spec && fl == F_DG_RES) return launch_pair_impl<8, false, true, F_DG_RES>(st, A, B, args);
         return launch_pair_impl<8, false, true>(st, A, B, args);
     }
     if (spec && fl == F_QKV) return launch_pair_impl<8, false, false, F_QKV>(st, A, B, args);
     if (spec && fl == F_CONV) return launch_pair_impl<8, false, false, F_CONV>(st, A, B, args);
     if (spec && fl == F_CONV_SAVE) return launch_pair_impl<8, false, false, F_CONV_SAVE>(st, A, B, args);
     if (spec && fl == F_LIN_H16) return launch_pair_impl<8, false, false, F_LIN_H16>(st, A, B, args);
+    if (spec && fl == F_DG_AUX) return launch_pair_impl<8, false, false, F_DG_AUX>(st, A, B, args);
+    if (spec && fl == F_H16) return launch_pair_impl<8, false, false, F_H16>(st, A, B, args);
     return launch_pair_impl<8, false>(st, A, B, args);
 }
 
