@@ -394,9 +394,11 @@ def test_triplet_step_gradients_against_autograd(record):
     va, vb = torch.cat([ours[k] for k in keep]), torch.cat([ref[k] for k in keep])
     g_rel = float((va - vb).norm() / vb.norm())
     g_cos = float((va @ vb) / (va.norm() * vb.norm()))
+    # how close the tightest per-tensor check ran to its bound (diff / (3 % |ref| + 0.1 % median norm)); < 1 passes
+    tight = max(((diff / (3e-2 * nb + 1e-3 * med)), k) for rel, cos, k, nb, diff in table)
     record("triplet_step", loss=loss.item(), loss_rel_err=rel_loss, all_grads_rel_l2=g_rel, all_grads_cosine=g_cos,
            worst_tensor_rel_l2=worst_rel, worst_tensor=worst_name, worst_tensor_cosine=worst_cos, tensors=len(names),
-           median_tensor_grad_norm=med)
+           median_tensor_grad_norm=med, tightest_check_fraction_of_bound=tight[0], tightest_check_tensor=tight[1])
     assert rel_loss <= 1e-3
     assert g_rel <= 2.5e-2 and g_cos >= 0.9997
 
