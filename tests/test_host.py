@@ -202,3 +202,17 @@ def test_native_wav_reader_against_the_wave_module(tmp_path):
     for i, pcm in enumerate(data):
         np.testing.assert_array_equal(buf[dst[i]: dst[i] + ns[i]], pcm.reshape(-1))
     assert (buf[int(ns.sum()):] == 12345).all()
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """Doc-drift guard: each NOMAD_B200_* variable the native sources read appears in INTEGRATION.md's table."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for path in glob.glob(os.path.join(root, "nomad_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "nomad_b200", "csrc", "*.cuh")):
+        names |= set(re.findall(r'getenv\("(NOMAD_B200_[A-Z0-9_]+)"\)', open(path).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert names, "no switches found: the scan is broken"
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
